@@ -1,0 +1,208 @@
+/* pharmsol_cuda.h — C ABI of the B200-native psi-matrix backend for LAPKB/pharmsol.
+ *
+ * This is the drop-in boundary a `simulator::cuda` backend inside pharmsol binds over FFI (see
+ * INTEGRATION.md for the Rust `extern "C"` block and the `impl Equation` glue).  All citations are
+ * file:line relative to the pharmsol source tree (v0.28.8).
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = ok, otherwise a PCU_ERR_* code that maps 1:1 onto a
+ *     `PharmsolError` / `ErrorModelError` variant (src/error/mod.rs:14-49);
+ *   - out-parameters by pointer; host buffers are caller-owned; device buffers live behind the
+ *     opaque handles and are freed by the matching *_destroy / *_free;
+ *   - handles are safe to use from several host threads (one internal lock per context), matching
+ *     `Equation: Sync` (src/simulator/equation/mod.rs:377);
+ *   - nothing here ever aborts or traps: the reference's `panic!`s on this path (imaginary roots,
+ *     missing covariates, particle-filter likelihood errors) become status codes;
+ *   - there is NO CPU fallback: every compute entry point fails with PCU_ERR_CUDA when no sm_100
+ *     device / driver is present.
+ *   - all arithmetic is FP64.
+ */
+#ifndef PHARMSOL_CUDA_H
+#define PHARMSOL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHARMSOL_CUDA_ABI_VERSION 1
+
+/* ---- status codes (== PharmsolError variants, src/error/mod.rs:14-49) ------------------------ */
+enum {
+    PCU_OK = 0,
+    PCU_ERR_NON_FINITE_LIKELIHOOD = 1,      /* PharmsolError::NonFiniteLikelihood          prediction.rs:120-124 */
+    PCU_ERR_NEGATIVE_SIGMA = 2,             /* ErrorModelError::NegativeSigma              error_model.rs:1073   */
+    PCU_ERR_NON_FINITE_SIGMA = 3,           /* ErrorModelError::NonFiniteSigma             error_model.rs:1075   */
+    PCU_ERR_INVALID_OUTPUT_EQUATION = 4,    /* ErrorModelError::InvalidOutputEquation      error_model.rs:679    */
+    PCU_ERR_NONE_ERROR_MODEL = 5,           /* ErrorModelError::NoneErrorModel             error_model.rs:682    */
+    PCU_ERR_MISSING_ERROR_MODEL = 6,        /* ErrorModelError::MissingErrorModel          error_model.rs:1067   */
+    PCU_ERR_SOLVER_FAILURE = 7,             /* PharmsolError::DiffsolError (from_solver_error)                  */
+    PCU_ERR_INPUT_OUT_OF_RANGE = 8,         /* PharmsolError::InputOutOfRange                                    */
+    PCU_ERR_OUTEQ_OUT_OF_RANGE = 9,         /* PharmsolError::OuteqOutOfRange                                    */
+    PCU_ERR_UNKNOWN_INPUT_LABEL = 10,       /* PharmsolError::UnknownInputLabel                                  */
+    PCU_ERR_UNKNOWN_OUTPUT_LABEL = 11,      /* PharmsolError::UnknownOutputLabel                                 */
+    PCU_ERR_IMAGINARY_ROOTS = 12,           /* replaces panic!  two_compartment_models.rs:20-22, three_...:32-34 */
+    PCU_ERR_UNSUPPORTED_INPUT_ROUTE_KIND = 13, /* PharmsolError::UnsupportedInputRouteKind                       */
+    PCU_ERR_MISSING_COVARIATE = 14,
+    PCU_ERR_OTHER = 15,                     /* PharmsolError::OtherError (message in last_error_message)         */
+    /* library-level */
+    PCU_ERR_CUDA = 64,                      /* CUDA runtime / driver failure, or no device                       */
+    PCU_ERR_COMPILE = 65,                   /* DSL parse / analysis error or NVRTC compile error                 */
+    PCU_ERR_INVALID_ARGUMENT = 66
+};
+
+/* ---- enums ------------------------------------------------------------------------------------ */
+enum { PCU_KIND_ODE = 0, PCU_KIND_ANALYTICAL = 1, PCU_KIND_SDE = 2 };        /* EqnKind, equation/mod.rs:580-586 */
+enum { PCU_CENSOR_NONE = 0, PCU_CENSOR_BLOQ = 1, PCU_CENSOR_ALOQ = 2 };      /* Censor, data/event.rs:559-567    */
+enum { PCU_ERRMODEL_NONE = 0, PCU_ERRMODEL_ADDITIVE = 1, PCU_ERRMODEL_PROPORTIONAL = 2 }; /* error_model.rs:786 */
+/* OdeSolver (ode/mod.rs:59-84).  The reference offers Bdf | Sdirk(TrBdf2|Esdirk34) | ExplicitRk(Tsit45)
+ * through diffsol; this backend offers two explicit and two implicit register-resident solvers. */
+enum { PCU_SOLVER_DOPRI5 = 0, PCU_SOLVER_TSIT45 = 1, PCU_SOLVER_SDIRK4 = 2, PCU_SOLVER_TRBDF2 = 3 };
+/* Analytical `derive` time semantics: sub-interval END (DSL runtime,
+ * dsl/native.rs:1903-1916) or sub-interval LENGTH (analytical! macro, analytical/mod.rs:362-364). */
+enum { PCU_COVTIME_INTERVAL_END = 0, PCU_COVTIME_INTERVAL_LENGTH = 1 };
+/* SDE likelihood mode: what log_likelihood_matrix does (mean prediction,
+ * sde/mod.rs:387-433) or SDE::estimate_log_likelihood (particle filter, sde/mod.rs:526-577). */
+enum { PCU_SDE_MEAN_PREDICTION = 0, PCU_SDE_PARTICLE_FILTER = 1 };
+enum { PCU_EM_REFERENCE_ADAPTIVE = 0, PCU_EM_FIXED_STEP = 1 };               /* sde/em.rs:134-167 vs fixed dt     */
+
+typedef struct pcu_ctx pcu_ctx;
+typedef struct pcu_model pcu_model;
+typedef struct pcu_subject_builder pcu_subject_builder;
+typedef struct pcu_subject pcu_subject;
+typedef struct pcu_data pcu_data;
+typedef struct pcu_population pcu_population;
+
+/* AssayErrorModel for one output equation (data/error_model.rs:786-812): sigma is computed from
+ * the OBSERVATION: alpha = c0 + c1 o + c2 o^2 + c3 o^3; additive sqrt(alpha^2 + factor^2);
+ * proportional factor * alpha (error_model.rs:1045-1080). */
+typedef struct pcu_error_model {
+    int32_t kind;        /* PCU_ERRMODEL_* */
+    int32_t pad;
+    double factor;       /* lambda (additive) or gamma (proportional) */
+    double c0, c1, c2, c3;
+} pcu_error_model;
+
+/* ---- library / context -------------------------------------------------------------------------- */
+int32_t pharmsol_cuda_abi_version(void);
+int32_t pharmsol_cuda_device_count(int32_t* n);
+int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out);
+void    pharmsol_cuda_ctx_destroy(pcu_ctx* ctx);
+/* message of the last failure on this thread (valid until the next failing call on the thread) */
+const char* pharmsol_cuda_last_error_message(void);
+/* kernel launches issued by this context so far; device time (ms, CUDA events on the launch stream)
+ * and work counters {accepted steps, rejected steps, rhs/kernel evaluations, Newton iterations}
+ * of the most recent psi launch */
+int64_t pharmsol_cuda_launch_count(pcu_ctx* ctx);
+double  pharmsol_cuda_last_kernel_ms(pcu_ctx* ctx);
+int32_t pharmsol_cuda_last_counters(pcu_ctx* ctx, uint64_t out[4]);
+/* pinned host memory for the caller's support-point / psi buffers */
+int32_t pharmsol_cuda_host_alloc(size_t bytes, void** out);
+int32_t pharmsol_cuda_host_free(void* p);
+
+/* ---- data: Subject::builder (src/data/builder.rs:84-362) ------------------------------------------ */
+pcu_subject_builder* pharmsol_subject_builder_new(const char* id);
+void pharmsol_subject_builder_bolus(pcu_subject_builder* b, double time, double amount, const char* input);
+void pharmsol_subject_builder_infusion(pcu_subject_builder* b, double time, double amount, const char* input, double duration);
+void pharmsol_subject_builder_observation(pcu_subject_builder* b, double time, double value, const char* outeq);
+void pharmsol_subject_builder_censored_observation(pcu_subject_builder* b, double time, double value, const char* outeq, int32_t censoring);
+void pharmsol_subject_builder_missing_observation(pcu_subject_builder* b, double time, const char* outeq);
+void pharmsol_subject_builder_observation_with_error(pcu_subject_builder* b, double time, double value, const char* outeq,
+                                                     double c0, double c1, double c2, double c3, int32_t censoring);
+void pharmsol_subject_builder_covariate(pcu_subject_builder* b, const char* name, double time, double value);
+void pharmsol_subject_builder_repeat(pcu_subject_builder* b, int64_t n, double delta);
+void pharmsol_subject_builder_reset(pcu_subject_builder* b);            /* next occasion */
+pcu_subject* pharmsol_subject_builder_build(pcu_subject_builder* b);    /* consumes the builder */
+/* Covariate::set_fixed (data/covariate.rs:243-248): carry-forward instead of linear interpolation */
+int32_t pharmsol_subject_set_covariate_fixed(pcu_subject* s, int32_t occasion, const char* name, int32_t fixed);
+void pharmsol_subject_free(pcu_subject* s);
+pcu_data* pharmsol_data_new(void);                                      /* Data::new (data/structs.rs:38) */
+int32_t pharmsol_data_add_subject(pcu_data* d, const pcu_subject* s);   /* copies */
+int64_t pharmsol_data_len(const pcu_data* d);
+void pharmsol_data_free(pcu_data* d);
+
+/* ---- models ----------------------------------------------------------------------------------------- */
+/* Compile a pharmsol-dsl source (authoring shorthand or canonical `model {}` form) to a device model:
+ * DSL -> IR -> CUDA C -> (AOT registry | on-disk cubin cache | NVRTC) -> module.
+ * Counterpart of compile_module_source_to_runtime(..., RuntimeCompilationTarget::*) src/dsl/runtime.rs:118-245.
+ * Parsing and code generation happen here; the device module is built lazily at the first launch
+ * (or by pharmsol_cuda_model_compile). */
+int32_t pharmsol_cuda_model_from_dsl(pcu_ctx* ctx, const char* source, size_t len, pcu_model** out);
+void    pharmsol_cuda_model_destroy(pcu_model* m);
+int32_t pharmsol_cuda_model_kind(const pcu_model* m);                   /* PCU_KIND_* */
+int32_t pharmsol_cuda_model_nparams(const pcu_model* m);
+int32_t pharmsol_cuda_model_nstates(const pcu_model* m);
+int32_t pharmsol_cuda_model_nouteqs(const pcu_model* m);
+const char* pharmsol_cuda_model_info_json(const pcu_model* m);          /* NativeModelInfo mirror, dsl/model_info.rs:17-92 */
+const char* pharmsol_cuda_model_cuda_source(const pcu_model* m);        /* the generated CUDA C translation unit */
+const char* pharmsol_cuda_model_id(const pcu_model* m);
+/* with_solver / with_tolerances (ode/mod.rs:135-166); defaults Dopri5, rtol = atol = 1e-4 (ode/mod.rs:40-41) */
+int32_t pharmsol_cuda_model_set_solver(pcu_model* m, int32_t solver, double rtol, double atol);
+int32_t pharmsol_cuda_model_set_max_steps(pcu_model* m, int32_t max_steps);
+/* with_particles (dsl/native.rs:2162) + stream seed + likelihood / stepper modes */
+int32_t pharmsol_cuda_model_set_particles(pcu_model* m, uint32_t nparticles, uint64_t seed, int32_t sde_mode,
+                                          int32_t em_mode, double em_dt);
+int32_t pharmsol_cuda_model_set_cov_time(pcu_model* m, int32_t cov_time);
+/* build (or fetch) the device module now; returns the NVRTC log in last_error_message on failure.
+ * *source_out (optional): 0 = ahead-of-time (nvcc, linked in), 1 = cubin cache, 2 = NVRTC */
+int32_t pharmsol_cuda_model_compile(pcu_ctx* ctx, pcu_model* m, int32_t* source_out);
+/* NVRTC-only: compile to a cubin without touching a device (used by the build step) */
+int32_t pharmsol_cuda_model_precompile_to_cache(pcu_model* m, int32_t solver);
+
+/* ---- population: flattened Data resident in HBM ------------------------------------------------------ */
+/* Resolve labels against the model's routes / outputs (equation/mod.rs:192-273, dsl/native.rs:663-770),
+ * precompute the per-observation sigma terms from `error_models` (may be NULL for predictions only),
+ * flatten into the SoA buffers of csrc/device/psi_types.h and upload. */
+int32_t pharmsol_cuda_population_create(pcu_ctx* ctx, const pcu_model* m, const pcu_data* d,
+                                        const pcu_error_model* error_models, int32_t n_error_models,
+                                        pcu_population** out);
+int32_t pharmsol_cuda_population_set_error_models(pcu_population* pop, const pcu_error_model* error_models, int32_t n);
+void    pharmsol_cuda_population_destroy(pcu_population* pop);
+int64_t pharmsol_cuda_population_nsubjects(const pcu_population* pop);
+int64_t pharmsol_cuda_population_nobservations(const pcu_population* pop);   /* prediction rows */
+/* prefix sums of per-subject observation counts, nsub+1 entries (ragged prediction layout) */
+int32_t pharmsol_cuda_population_obs_offsets(const pcu_population* pop, int64_t* out);
+int64_t pharmsol_cuda_population_device_bytes(const pcu_population* pop);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+/* log_likelihood_matrix (src/simulator/likelihood/matrix.rs:52-106).
+ *   support_points  host, row-major (nspp x nparams): rows = support points, cols = parameters in model order
+ *   out             host, column-major / F-order (nsub x nspp)          (matrix.rs:60)
+ * The first failing pair aborts the result like matrix.rs:96-104: the call returns that pair's code,
+ * *first_error_pair = i + j*nsub (either pointer may be NULL), and `out` holds NaN for failing pairs. */
+int32_t pharmsol_cuda_log_likelihood_matrix(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                            const double* support_points, int64_t nspp, int32_t nparams,
+                                            double* out, int32_t* first_error_code, int64_t* first_error_pair);
+/* Same with everything resident in HBM (no copies in the call):
+ *   spp_soa_dev   device, parameter-major SoA: spp[k*ld_spp + j]
+ *   out_dev       device, column-major: out[i + j*ld_out], ld_out >= nsub
+ *   stream        cudaStream_t to launch on (NULL = the context's stream); the call is asynchronous,
+ *                 errors of the launch are collected by pharmsol_cuda_collect_errors after a sync. */
+int32_t pharmsol_cuda_log_likelihood_matrix_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                                   const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                                                   double* out_dev, int64_t ld_out, int64_t first_col, void* stream);
+int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* first_error_code, int64_t* first_error_pair);
+/* row-major host support points -> SoA device buffer (H2D + on-device transpose) */
+int32_t pharmsol_cuda_upload_support_points(pcu_ctx* ctx, const double* support_points, int64_t nspp, int32_t nparams,
+                                            double* spp_soa_dev, int64_t ld_spp, void* stream);
+/* estimate_predictions for every (subject, support point) pair (equation/mod.rs:526-532):
+ *   out  host, (nobs_total x nspp) row-major: out[row*nspp + j], row = obs_offsets[i] + k-th observation of subject i
+ * Missing observations are included (they are prediction slots). */
+int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                  const double* support_points, int64_t nspp, int32_t nparams, double* out);
+int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                         const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                                         double* pred_dev, int64_t ld_pred, double* ll_dev_or_null, int64_t ld_out, void* stream);
+/* psi / log_psi deprecated wrappers (matrix.rs:117-150): exp of the log matrix, on device */
+int32_t pharmsol_cuda_psi(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* support_points, int64_t nspp,
+                          int32_t nparams, double* out, int32_t* first_error_code, int64_t* first_error_pair);
+
+/* measured FP64 FMA throughput of this device (register-resident DFMA chains), TFLOP/s */
+int32_t pharmsol_cuda_measure_fp64_peak(pcu_ctx* ctx, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHARMSOL_CUDA_H */

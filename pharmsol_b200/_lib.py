@@ -1,0 +1,385 @@
+"""ctypes binding of ``libpharmsol_cuda.so`` — every call goes through the C ABI declared in
+``include/pharmsol_cuda.h``.  No torch types cross this boundary (raw pointers and sizes only).
+
+The product never imports ``oracle``; if the shared library is missing the import fails loudly
+(there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpharmsol_cuda.so")
+
+ERROR_NAMES = {
+    0: "Ok", 1: "NonFiniteLikelihood", 2: "NegativeSigma", 3: "NonFiniteSigma", 4: "InvalidOutputEquation",
+    5: "NoneErrorModel", 6: "MissingErrorModel", 7: "SolverFailure", 8: "InputOutOfRange", 9: "OuteqOutOfRange",
+    10: "UnknownInputLabel", 11: "UnknownOutputLabel", 12: "ImaginaryRoots", 13: "UnsupportedInputRouteKind",
+    14: "MissingCovariate", 15: "OtherError", 64: "CudaError", 65: "CompileError", 66: "InvalidArgument",
+}
+
+
+class PharmsolError(RuntimeError):
+    """Mirror of ``pharmsol::PharmsolError`` (src/error/mod.rs:14-49): ``code`` is the C-ABI status,
+    ``variant`` the Rust variant name, ``pair`` the failing ``i + j*nsub`` when known."""
+
+    def __init__(self, code, message="", pair=None):
+        self.code = int(code)
+        self.variant = ERROR_NAMES.get(self.code, f"Error{code}")
+        self.pair = pair
+        super().__init__(f"{self.variant}: {message}" if message else self.variant)
+
+
+class pcu_error_model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("factor", C.c_double),
+                ("c0", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("c3", C.c_double)]
+
+
+def declared_symbols():
+    """Every function name declared in include/pharmsol_cuda.h (parsed from the header)."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "pharmsol_cuda.h")
+    text = open(hdr).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pharmsol_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pharmsol_b200.build` (nvcc, sm_100a). "
+            "pharmsol_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, d, i32, i64, cs, sz = C.c_void_p, C.c_double, C.c_int32, C.c_int64, C.c_char_p, C.c_size_t
+    dp = C.POINTER(C.c_double)
+    P = C.POINTER
+    sig = {
+        "pharmsol_cuda_abi_version": (i32, []),
+        "pharmsol_cuda_device_count": (i32, [P(i32)]),
+        "pharmsol_cuda_ctx_create": (i32, [i32, P(vp)]),
+        "pharmsol_cuda_ctx_destroy": (None, [vp]),
+        "pharmsol_cuda_last_error_message": (cs, []),
+        "pharmsol_cuda_launch_count": (i64, [vp]),
+        "pharmsol_cuda_last_kernel_ms": (d, [vp]),
+        "pharmsol_cuda_last_counters": (i32, [vp, P(C.c_uint64)]),
+        "pharmsol_cuda_host_alloc": (i32, [sz, P(vp)]),
+        "pharmsol_cuda_host_free": (i32, [vp]),
+        "pharmsol_subject_builder_new": (vp, [cs]),
+        "pharmsol_subject_builder_bolus": (None, [vp, d, d, cs]),
+        "pharmsol_subject_builder_infusion": (None, [vp, d, d, cs, d]),
+        "pharmsol_subject_builder_observation": (None, [vp, d, d, cs]),
+        "pharmsol_subject_builder_censored_observation": (None, [vp, d, d, cs, i32]),
+        "pharmsol_subject_builder_missing_observation": (None, [vp, d, cs]),
+        "pharmsol_subject_builder_observation_with_error": (None, [vp, d, d, cs, d, d, d, d, i32]),
+        "pharmsol_subject_builder_covariate": (None, [vp, cs, d, d]),
+        "pharmsol_subject_builder_repeat": (None, [vp, i64, d]),
+        "pharmsol_subject_builder_reset": (None, [vp]),
+        "pharmsol_subject_builder_build": (vp, [vp]),
+        "pharmsol_subject_set_covariate_fixed": (i32, [vp, i32, cs, i32]),
+        "pharmsol_subject_free": (None, [vp]),
+        "pharmsol_data_new": (vp, []),
+        "pharmsol_data_add_subject": (i32, [vp, vp]),
+        "pharmsol_data_len": (i64, [vp]),
+        "pharmsol_data_free": (None, [vp]),
+        "pharmsol_cuda_model_from_dsl": (i32, [vp, cs, sz, P(vp)]),
+        "pharmsol_cuda_model_destroy": (None, [vp]),
+        "pharmsol_cuda_model_kind": (i32, [vp]),
+        "pharmsol_cuda_model_nparams": (i32, [vp]),
+        "pharmsol_cuda_model_nstates": (i32, [vp]),
+        "pharmsol_cuda_model_nouteqs": (i32, [vp]),
+        "pharmsol_cuda_model_info_json": (cs, [vp]),
+        "pharmsol_cuda_model_cuda_source": (cs, [vp]),
+        "pharmsol_cuda_model_id": (cs, [vp]),
+        "pharmsol_cuda_model_set_solver": (i32, [vp, i32, d, d]),
+        "pharmsol_cuda_model_set_max_steps": (i32, [vp, i32]),
+        "pharmsol_cuda_model_set_particles": (i32, [vp, C.c_uint32, C.c_uint64, i32, i32, d]),
+        "pharmsol_cuda_model_set_cov_time": (i32, [vp, i32]),
+        "pharmsol_cuda_model_compile": (i32, [vp, vp, P(i32)]),
+        "pharmsol_cuda_model_precompile_to_cache": (i32, [vp, i32]),
+        "pharmsol_cuda_population_create": (i32, [vp, vp, vp, P(pcu_error_model), i32, P(vp)]),
+        "pharmsol_cuda_population_set_error_models": (i32, [vp, P(pcu_error_model), i32]),
+        "pharmsol_cuda_population_destroy": (None, [vp]),
+        "pharmsol_cuda_population_nsubjects": (i64, [vp]),
+        "pharmsol_cuda_population_nobservations": (i64, [vp]),
+        "pharmsol_cuda_population_obs_offsets": (i32, [vp, P(i64)]),
+        "pharmsol_cuda_population_device_bytes": (i64, [vp]),
+        "pharmsol_cuda_log_likelihood_matrix": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
+        "pharmsol_cuda_log_likelihood_matrix_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, i64, vp]),
+        "pharmsol_cuda_collect_errors": (i32, [vp, P(i32), P(i64)]),
+        "pharmsol_cuda_upload_support_points": (i32, [vp, dp, i64, i32, vp, i64, vp]),
+        "pharmsol_cuda_predictions": (i32, [vp, vp, vp, dp, i64, i32, dp]),
+        "pharmsol_cuda_predictions_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, i64, vp]),
+        "pharmsol_cuda_psi": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
+        "pharmsol_cuda_measure_fp64_peak": (i32, [vp, dp, dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+def _msg():
+    m = lib().pharmsol_cuda_last_error_message()
+    return m.decode(errors="replace") if m else ""
+
+
+def check(rc, pair=None):
+    if rc != 0:
+        raise PharmsolError(rc, _msg(), pair)
+
+
+def _b(s):
+    return str(s).encode()
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def device_count():
+    n = C.c_int32(0)
+    check(lib().pharmsol_cuda_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    def __init__(self, device=0):
+        self.ptr = C.c_void_p()
+        check(lib().pharmsol_cuda_ctx_create(int(device), C.byref(self.ptr)))
+        self.device = int(device)
+
+    def close(self):
+        if self.ptr:
+            lib().pharmsol_cuda_ctx_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    @property
+    def launch_count(self):
+        return lib().pharmsol_cuda_launch_count(self.ptr)
+
+    @property
+    def last_kernel_ms(self):
+        return lib().pharmsol_cuda_last_kernel_ms(self.ptr)
+
+    @property
+    def last_counters(self):
+        out = (C.c_uint64 * 4)()
+        check(lib().pharmsol_cuda_last_counters(self.ptr, out))
+        return {"steps": out[0], "rejected": out[1], "evals": out[2], "newton": out[3]}
+
+    def measure_fp64_peak(self):
+        t, clk = C.c_double(), C.c_double()
+        check(lib().pharmsol_cuda_measure_fp64_peak(self.ptr, C.byref(t), C.byref(clk)))
+        return t.value, clk.value
+
+    def collect_errors(self):
+        code, pair = C.c_int32(0), C.c_int64(-1)
+        rc = lib().pharmsol_cuda_collect_errors(self.ptr, C.byref(code), C.byref(pair))
+        if rc != 0:
+            raise PharmsolError(rc, _msg(), pair.value)
+
+
+_contexts = {}
+
+
+def context(device=0):
+    device = int(device)
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+CENSOR = {None: 0, "none": 0, "None": 0, "bloq": 1, "BLOQ": 1, "aloq": 2, "ALOQ": 2, 0: 0, 1: 1, 2: 2}
+
+
+class NativeSubject:
+    """Builds a pcu_subject from builder ops (see Subject.ops in api.py)."""
+
+    def __init__(self, id, ops):
+        L = lib()
+        b = L.pharmsol_subject_builder_new(_b(id))
+        fixed = []
+        for op in ops:
+            k = op[0]
+            if k == "bolus":
+                L.pharmsol_subject_builder_bolus(b, op[1], op[2], _b(op[3]))
+            elif k == "infusion":
+                L.pharmsol_subject_builder_infusion(b, op[1], op[2], _b(op[3]), op[4])
+            elif k == "observation":
+                L.pharmsol_subject_builder_observation(b, op[1], op[2], _b(op[3]))
+            elif k == "missing_observation":
+                L.pharmsol_subject_builder_missing_observation(b, op[1], _b(op[2]))
+            elif k == "censored_observation":
+                L.pharmsol_subject_builder_censored_observation(b, op[1], op[2], _b(op[3]), CENSOR[op[4]])
+            elif k == "observation_with_error":
+                c = op[4]
+                L.pharmsol_subject_builder_observation_with_error(b, op[1], op[2], _b(op[3]), c[0], c[1], c[2], c[3], CENSOR[op[5]])
+            elif k == "covariate":
+                L.pharmsol_subject_builder_covariate(b, _b(op[1]), op[2], op[3])
+            elif k == "repeat":
+                L.pharmsol_subject_builder_repeat(b, int(op[1]), float(op[2]))
+            elif k == "reset":
+                L.pharmsol_subject_builder_reset(b)
+            elif k == "covariate_fixed":
+                fixed.append(op)
+            else:
+                raise ValueError(f"unknown subject op {op!r}")
+        self.ptr = C.c_void_p(L.pharmsol_subject_builder_build(b))
+        for op in fixed:
+            check(L.pharmsol_subject_set_covariate_fixed(self.ptr, int(op[1]), _b(op[2]), int(bool(op[3]))))
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.pharmsol_subject_free(self.ptr)
+            self.ptr = None
+
+
+class NativeData:
+    def __init__(self, subjects):
+        L = lib()
+        self.ptr = C.c_void_p(L.pharmsol_data_new())
+        for s in subjects:
+            ns = NativeSubject(s.id, s.ops)
+            check(L.pharmsol_data_add_subject(self.ptr, ns.ptr))
+
+    def __len__(self):
+        return lib().pharmsol_data_len(self.ptr)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.pharmsol_data_free(self.ptr)
+            self.ptr = None
+
+
+class Model:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    @classmethod
+    def from_dsl(cls, source):
+        src = source.encode()
+        ptr = C.c_void_p()
+        check(lib().pharmsol_cuda_model_from_dsl(None, src, len(src), C.byref(ptr)))
+        return cls(ptr)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.pharmsol_cuda_model_destroy(self.ptr)
+            self.ptr = None
+
+    kind = property(lambda self: lib().pharmsol_cuda_model_kind(self.ptr))
+    nparams = property(lambda self: lib().pharmsol_cuda_model_nparams(self.ptr))
+    nstates = property(lambda self: lib().pharmsol_cuda_model_nstates(self.ptr))
+    nouteqs = property(lambda self: lib().pharmsol_cuda_model_nouteqs(self.ptr))
+    id = property(lambda self: lib().pharmsol_cuda_model_id(self.ptr).decode())
+    cuda_source = property(lambda self: lib().pharmsol_cuda_model_cuda_source(self.ptr).decode())
+
+    @property
+    def info(self):
+        import json
+        return json.loads(lib().pharmsol_cuda_model_info_json(self.ptr).decode())
+
+    def set_solver(self, solver, rtol, atol):
+        check(lib().pharmsol_cuda_model_set_solver(self.ptr, int(solver), float(rtol), float(atol)))
+
+    def set_max_steps(self, n):
+        check(lib().pharmsol_cuda_model_set_max_steps(self.ptr, int(n)))
+
+    def set_particles(self, n, seed=0, sde_mode=0, em_mode=0, em_dt=0.0):
+        check(lib().pharmsol_cuda_model_set_particles(self.ptr, int(n), int(seed), int(sde_mode), int(em_mode), float(em_dt)))
+
+    def set_cov_time(self, mode):
+        check(lib().pharmsol_cuda_model_set_cov_time(self.ptr, int(mode)))
+
+    def compile(self, ctx):
+        src = C.c_int32(-1)
+        check(lib().pharmsol_cuda_model_compile(ctx.ptr, self.ptr, C.byref(src)))
+        return {0: "aot", 1: "cubin-cache", 2: "nvrtc"}[src.value]
+
+    def precompile_to_cache(self, solver=0):
+        check(lib().pharmsol_cuda_model_precompile_to_cache(self.ptr, int(solver)))
+
+
+def _em_array(error_models):
+    """error_models: list of None | (kind:int, factor, (c0,c1,c2,c3)) per output equation."""
+    n = len(error_models)
+    arr = (pcu_error_model * max(n, 1))()
+    for i, m in enumerate(error_models):
+        if m is None:
+            arr[i].kind = 0
+            continue
+        kind, factor, poly = m
+        arr[i].kind = int(kind)
+        arr[i].factor = float(factor)
+        arr[i].c0, arr[i].c1, arr[i].c2, arr[i].c3 = [float(c) for c in poly]
+    return arr, n
+
+
+class Population:
+    def __init__(self, ctx, model, data, error_models=None):
+        self.ptr = C.c_void_p()
+        self.ctx = ctx
+        if error_models:
+            arr, n = _em_array(error_models)
+        else:
+            arr, n = None, 0
+        check(lib().pharmsol_cuda_population_create(ctx.ptr, model.ptr, data.ptr, arr, n, C.byref(self.ptr)))
+
+    def set_error_models(self, error_models):
+        if error_models:
+            arr, n = _em_array(error_models)
+        else:
+            arr, n = None, 0
+        check(lib().pharmsol_cuda_population_set_error_models(self.ptr, arr, n))
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.pharmsol_cuda_population_destroy(self.ptr)
+            self.ptr = None
+
+    nsubjects = property(lambda self: lib().pharmsol_cuda_population_nsubjects(self.ptr))
+    nobservations = property(lambda self: lib().pharmsol_cuda_population_nobservations(self.ptr))
+    device_bytes = property(lambda self: lib().pharmsol_cuda_population_device_bytes(self.ptr))
+
+    def obs_offsets(self):
+        out = (C.c_int64 * (self.nsubjects + 1))()
+        check(lib().pharmsol_cuda_population_obs_offsets(self.ptr, out))
+        return np.array(out[:], dtype=np.int64)
+
+
+def log_likelihood_matrix(ctx, model, pop, support_points, out=None, exponentiate=False):
+    """Host-buffer call: row-major (nspp, P) in, F-order (nsub, nspp) out."""
+    spp = np.ascontiguousarray(support_points, dtype=np.float64)
+    if spp.ndim != 2:
+        raise PharmsolError(66, "support_points must be 2-D (rows = support points)")
+    nspp, npar = spp.shape
+    nsub = pop.nsubjects
+    if out is None:
+        out = np.empty((nsub, nspp), dtype=np.float64, order="F")
+    code, pair = C.c_int32(0), C.c_int64(-1)
+    fn = lib().pharmsol_cuda_psi if exponentiate else lib().pharmsol_cuda_log_likelihood_matrix
+    rc = fn(ctx.ptr, model.ptr, pop.ptr, _dp(spp), nspp, npar, _dp(out), C.byref(code), C.byref(pair))
+    if rc != 0:
+        raise PharmsolError(rc, _msg(), pair.value if pair.value >= 0 else None)
+    return out
+
+
+def predictions(ctx, model, pop, support_points):
+    """(nobs_total, nspp) row-major predictions for every pair."""
+    spp = np.ascontiguousarray(support_points, dtype=np.float64)
+    nspp, npar = spp.shape
+    out = np.empty((pop.nobservations, nspp), dtype=np.float64)
+    check(lib().pharmsol_cuda_predictions(ctx.ptr, model.ptr, pop.ptr, _dp(spp), nspp, npar, _dp(out)))
+    return out

@@ -1,0 +1,507 @@
+"""Host-side mirror of pharmsol's public interface on the psi path.
+
+Same names, argument meaning and error behaviour as the reference (citations relative to
+/root/reference/src):
+
+  Subject.builder(..).bolus/.infusion/.observation/...      data/builder.rs:84-362
+  Data                                                       data/structs.rs:38
+  ErrorPoly, AssayErrorModel(s)                              data/error_model.rs:17,150,786
+  Equation.estimate_predictions / estimate_log_likelihood    simulator/equation/mod.rs:377-577
+  ODE.with_solver / with_tolerances, OdeSolver               simulator/equation/ode/mod.rs:59-166
+  log_likelihood_matrix / log_psi / psi                      simulator/likelihood/matrix.rs:52-150
+  ParameterOrder                                             parameter_order.rs
+
+Models are authored in pharmsol-dsl (text) — or with the `analytical()/ode()/sde()` builders that
+mirror the `analytical!/ode!/sde!` macro declarations (pharmsol-macros/src/expand/*.rs) with DSL
+expression strings in place of Rust closure bodies — and compiled to sm_100a device code.
+Everything numeric runs on the GPU through the C ABI (``_lib``); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import PharmsolError
+
+
+# ---------------------------------------------------------------------------------------------
+# data
+# ---------------------------------------------------------------------------------------------
+class Censor:
+    NONE = "none"
+    BLOQ = "bloq"
+    ALOQ = "aloq"
+
+
+class ErrorPoly:
+    def __init__(self, c0, c1, c2, c3):
+        self.c0, self.c1, self.c2, self.c3 = float(c0), float(c1), float(c2), float(c3)
+
+    @classmethod
+    def new(cls, c0, c1, c2, c3):
+        return cls(c0, c1, c2, c3)
+
+    def coefficients(self):
+        return (self.c0, self.c1, self.c2, self.c3)
+
+
+class Subject:
+    """A subject = id + the builder ops that produced it (replayed through the C ABI)."""
+
+    def __init__(self, id, ops):
+        self.id = str(id)
+        self.ops = list(ops)
+
+    @staticmethod
+    def builder(id):
+        return SubjectBuilder(id)
+
+
+class SubjectBuilder:
+    def __init__(self, id):
+        self.id = str(id)
+        self.ops = []
+
+    def bolus(self, time, amount, input):
+        self.ops.append(("bolus", float(time), float(amount), str(input)))
+        return self
+
+    def infusion(self, time, amount, input, duration):
+        self.ops.append(("infusion", float(time), float(amount), str(input), float(duration)))
+        return self
+
+    def observation(self, time, value, outeq):
+        self.ops.append(("observation", float(time), float(value), str(outeq)))
+        return self
+
+    def censored_observation(self, time, value, outeq, censoring):
+        self.ops.append(("censored_observation", float(time), float(value), str(outeq), censoring))
+        return self
+
+    def missing_observation(self, time, outeq):
+        self.ops.append(("missing_observation", float(time), str(outeq)))
+        return self
+
+    def observation_with_error(self, time, value, outeq, errorpoly, censored=Censor.NONE):
+        c = errorpoly.coefficients() if isinstance(errorpoly, ErrorPoly) else tuple(errorpoly)
+        self.ops.append(("observation_with_error", float(time), float(value), str(outeq), c, censored))
+        return self
+
+    def covariate(self, name, time, value):
+        self.ops.append(("covariate", str(name), float(time), float(value)))
+        return self
+
+    def repeat(self, n, delta):
+        self.ops.append(("repeat", int(n), float(delta)))
+        return self
+
+    def reset(self):
+        self.ops.append(("reset",))
+        return self
+
+    def fixed_covariate(self, occasion, name, fixed=True):
+        """Covariate::set_fixed (data/covariate.rs:243-248) on a built occasion."""
+        self.ops.append(("covariate_fixed", int(occasion), str(name), bool(fixed)))
+        return self
+
+    def build(self):
+        return Subject(self.id, self.ops)
+
+
+class Data:
+    def __init__(self, subjects: Iterable[Subject]):
+        self.subjects = list(subjects)
+        self._native = None
+
+    @classmethod
+    def new(cls, subjects):
+        return cls(subjects)
+
+    def __len__(self):
+        return len(self.subjects)
+
+    def native(self):
+        if self._native is None:
+            self._native = _lib.NativeData(self.subjects)
+        return self._native
+
+
+class AssayErrorModel:
+    NONE, ADDITIVE, PROPORTIONAL = 0, 1, 2
+
+    def __init__(self, kind, factor, poly):
+        self.kind, self.factor, self.poly = kind, float(factor), poly
+
+    @classmethod
+    def additive(cls, poly, lambda_):
+        return cls(cls.ADDITIVE, lambda_, poly)
+
+    @classmethod
+    def proportional(cls, poly, gamma):
+        return cls(cls.PROPORTIONAL, gamma, poly)
+
+    @classmethod
+    def none(cls):
+        return cls(cls.NONE, 0.0, ErrorPoly(0, 0, 0, 0))
+
+    def key(self):
+        return (self.kind, self.factor, self.poly.coefficients())
+
+
+class AssayErrorModels:
+    """Keyed by output label or dense index; bound to the equation's outputs at use time
+    (error_model.rs `bind_to`)."""
+
+    def __init__(self):
+        self.models = {}
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    def add(self, outeq, model):
+        if outeq in self.models:
+            raise PharmsolError(15, f"error model for output `{outeq}` already exists")
+        self.models[outeq] = model
+        return self
+
+    def bound(self, output_names):
+        """-> dense list indexed by output equation (None where absent)."""
+        dense = [None] * len(output_names)
+        for key, model in self.models.items():
+            if isinstance(key, (int, np.integer)):
+                idx = int(key)
+            else:
+                key = str(key)
+                if key in output_names:
+                    idx = output_names.index(key)
+                elif key.isdigit() and f"outeq_{key}" in output_names:
+                    idx = output_names.index(f"outeq_{key}")
+                elif key.isdigit():
+                    idx = int(key)
+                else:
+                    raise PharmsolError(11, f"unknown output label `{key}` (available: {', '.join(output_names)})")
+            if idx >= len(dense):
+                dense.extend([None] * (idx + 1 - len(dense)))
+            dense[idx] = model.key() if model.kind != AssayErrorModel.NONE else None
+        return dense
+
+
+# ---------------------------------------------------------------------------------------------
+# equations
+# ---------------------------------------------------------------------------------------------
+class OdeSolver:
+    """ode/mod.rs:59-84.  The reference's solvers come from diffsol; this backend provides two
+    explicit pairs and two implicit (stiff) methods.  `Bdf` (the reference default for stiff
+    problems) and `Esdirk34` select the order-4 SDIRK."""
+    Dopri5 = 0
+    Tsit45 = 1
+    Sdirk4 = 2
+    TrBdf2 = 3
+    Bdf = 2
+    Esdirk34 = 2
+
+
+class CovTime:
+    IntervalEnd = 0      # DSL runtime semantics (dsl/native.rs:1903-1916)
+    IntervalLength = 1   # analytical! macro semantics (analytical/mod.rs:362-364), SURVEY F5
+
+
+class SdeMode:
+    MeanPrediction = 0   # what log_likelihood_matrix evaluates (sde/mod.rs:387-433)
+    ParticleFilter = 1   # SDE::estimate_log_likelihood (sde/mod.rs:526-577, 689-736)
+
+
+class EmMode:
+    ReferenceAdaptive = 0
+    FixedStep = 1
+
+
+class EqnKind:
+    ODE, Analytical, SDE = 0, 1, 2
+
+
+class SubjectPredictions:
+    """likelihood/subject.rs:19: predictions of one subject for one support point."""
+
+    def __init__(self, times, observations, predictions):
+        self._t, self._o, self._p = times, observations, predictions
+
+    def flat_predictions(self):
+        return list(self._p)
+
+    def flat_times(self):
+        return list(self._t)
+
+    def flat_observations(self):
+        return list(self._o)
+
+
+class Equation:
+    def __init__(self, source, device=None):
+        self.source = source
+        self._model = _lib.Model.from_dsl(source)
+        self.info = self._model.info
+        self.device = device
+        self._pops = {}
+
+    # -- construction ---------------------------------------------------------------------------
+    @staticmethod
+    def from_dsl(source, device=None):
+        eq = Equation(source, device)
+        cls = {0: ODE, 1: Analytical, 2: SDE}[eq._model.kind]
+        eq.__class__ = cls
+        eq._post_init()
+        return eq
+
+    def _post_init(self):
+        pass
+
+    # -- introspection (equation/mod.rs:534-547) ----------------------------------------------------
+    def kind(self):
+        return self._model.kind
+
+    def nstates(self):
+        return self._model.nstates
+
+    def nouteqs(self):
+        return self._model.nouteqs
+
+    def nparams(self):
+        return self._model.nparams
+
+    def parameter_names(self):
+        return list(self.info["parameters"])
+
+    def output_names(self):
+        return list(self.info["outputs"])
+
+    @property
+    def cuda_source(self):
+        return self._model.cuda_source
+
+    # -- runtime ------------------------------------------------------------------------------------
+    def _ctx(self):
+        dev = self.device
+        if dev is None:
+            import os
+            dev = int(os.environ.get("LOCAL_RANK", "0")) if "PHARMSOL_B200_DEVICE" not in os.environ else int(os.environ["PHARMSOL_B200_DEVICE"])
+        return _lib.context(dev)
+
+    def population(self, data: Data, error_models: AssayErrorModels | None):
+        dense = error_models.bound(self.output_names()) if error_models is not None else None
+        key = (id(data), repr(dense))
+        pop = self._pops.get(key)
+        if pop is None:
+            if len(self._pops) > 8:
+                self._pops.clear()
+            pop = _lib.Population(self._ctx(), self._model, data.native(), dense)
+            self._pops[key] = (pop, data)   # keep `data` alive so id() stays unique
+            return pop
+        return pop[0]
+
+    def log_likelihood_matrix(self, data, support_points, error_models, exponentiate=False):
+        pop = self.population(data, error_models)
+        return _lib.log_likelihood_matrix(self._ctx(), self._model, pop, support_points, exponentiate=exponentiate)
+
+    def predictions_matrix(self, data, support_points):
+        """(nobs_total, nspp) predictions + per-subject row offsets."""
+        pop = self.population(data, None)
+        return _lib.predictions(self._ctx(), self._model, pop, support_points), pop.obs_offsets()
+
+    def estimate_predictions(self, subject: Subject, parameters) -> SubjectPredictions:
+        data = Data([subject])
+        p = np.asarray(parameters, dtype=np.float64).reshape(1, -1)
+        pred, _ = self.predictions_matrix(data, p)
+        return SubjectPredictions([], [], pred[:, 0].tolist())
+
+    def estimate_log_likelihood(self, subject: Subject, parameters, error_models: AssayErrorModels) -> float:
+        data = Data([subject])
+        p = np.asarray(parameters, dtype=np.float64).reshape(1, -1)
+        return float(self.log_likelihood_matrix(data, p, error_models)[0, 0])
+
+    def estimate_likelihood(self, subject, parameters, error_models):
+        warnings.warn("Use estimate_log_likelihood() instead for better numerical stability", DeprecationWarning)
+        return float(np.exp(self.estimate_log_likelihood(subject, parameters, error_models)))
+
+
+class Analytical(Equation):
+    def with_cov_time(self, mode):
+        self._model.set_cov_time(mode)
+        return self
+
+
+class ODE(Equation):
+    def _post_init(self):
+        self._solver, self._rtol, self._atol = OdeSolver.Dopri5, 1e-4, 1e-4   # RTOL/ATOL ode/mod.rs:40-41
+
+    def with_solver(self, solver):
+        self._solver = int(solver)
+        self._model.set_solver(self._solver, self._rtol, self._atol)
+        return self
+
+    def with_tolerances(self, rtol, atol):
+        self._rtol, self._atol = float(rtol), float(atol)
+        self._model.set_solver(self._solver, self._rtol, self._atol)
+        return self
+
+    def with_max_steps(self, n):
+        self._model.set_max_steps(n)
+        return self
+
+
+class SDE(Equation):
+    def _post_init(self):
+        self._np = int(self.info.get("particles") or 1000)
+        self._seed, self._mode, self._em, self._dt = 0x5EED, SdeMode.MeanPrediction, EmMode.ReferenceAdaptive, 0.05
+        self._apply()
+
+    def _apply(self):
+        self._model.set_particles(self._np, self._seed, self._mode, self._em, self._dt)
+
+    def with_particles(self, n):
+        self._np = int(n)
+        self._apply()
+        return self
+
+    def with_seed(self, seed):
+        self._seed = int(seed)
+        self._apply()
+        return self
+
+    def with_mode(self, mode):
+        self._mode = int(mode)
+        self._apply()
+        return self
+
+    def with_stepper(self, em_mode, dt=0.05):
+        self._em, self._dt = int(em_mode), float(dt)
+        self._apply()
+        return self
+
+    def estimate_log_likelihood(self, subject, parameters, error_models):
+        """SDE::estimate_log_likelihood runs the particle filter (sde/mod.rs:689-736)."""
+        saved = self._mode
+        try:
+            self.with_mode(SdeMode.ParticleFilter)
+            return Equation.estimate_log_likelihood(self, subject, parameters, error_models)
+        finally:
+            self.with_mode(saved)
+
+
+# ---------------------------------------------------------------------------------------------
+# macro-style builders: analytical!{...} / ode!{...} / sde!{...} with DSL expression strings
+# ---------------------------------------------------------------------------------------------
+def _authoring(name, kind, params, covariates, states, outputs, routes, derived, body_lines, particles=None, structure=None):
+    lines = [f"name = {name}", f"kind = {kind}", "params = " + ", ".join(params)]
+    if covariates:
+        lines.append("covariates = " + ", ".join(covariates))
+    lines.append("states = " + ", ".join(states))
+    if derived:
+        lines.append("derived = " + ", ".join(derived))
+    lines.append("outputs = " + ", ".join(outputs))
+    if particles:
+        lines.append(f"particles = {int(particles)}")
+    for r in routes:   # "bolus(oral) -> gut"
+        lines.append(r)
+    if structure:
+        lines.append(f"structure = {structure}")
+    lines.extend(body_lines)
+    return "\n".join(lines) + "\n"
+
+
+def _body(derive=None, lag=None, fa=None, init=None, out=None, dx=None, noise=None):
+    lines = []
+    for k, v in (derive or {}).items():
+        lines.append(f"{k} = {v}")
+    for k, v in (lag or {}).items():
+        lines.append(f"lag({k}) = {v}")
+    for k, v in (fa or {}).items():
+        lines.append(f"fa({k}) = {v}")
+    for k, v in (dx or {}).items():
+        lines.append(f"dx({k}) = {v}")
+    for k, v in (noise or {}).items():
+        lines.append(f"noise({k}) = {v}")
+    for k, v in (init or {}).items():
+        lines.append(f"init({k}) = {v}")
+    for k, v in (out or {}).items():
+        lines.append(f"out({k}) = {v} ~ continuous()")
+    return lines
+
+
+def analytical(name, params, states, outputs, routes, structure, out, covariates=(), derived=(), derive=None, lag=None, fa=None,
+               init=None, device=None):
+    """analytical!{ name, params, covariates, derived, states, outputs, routes, structure, derive, lag, fa, init, out }
+    (pharmsol-macros/src/expand/analytical.rs:31-135)."""
+    src = _authoring(name, "analytical", params, covariates, states, outputs, routes, derived,
+                     _body(derive=derive, lag=lag, fa=fa, init=init, out=out), structure=structure)
+    return Equation.from_dsl(src, device)
+
+
+def ode(name, params, states, outputs, routes, diffeq, out, covariates=(), derived=(), derive=None, lag=None, fa=None, init=None,
+        device=None):
+    """ode!{ ... diffeq: {state: expr}, out: {output: expr} } (pharmsol-macros/src/expand/ode.rs:126-185)."""
+    src = _authoring(name, "ode", params, covariates, states, outputs, routes, derived,
+                     _body(derive=derive, lag=lag, fa=fa, init=init, out=out, dx=diffeq))
+    return Equation.from_dsl(src, device)
+
+
+def sde(name, params, states, outputs, routes, drift, diffusion, out, particles, covariates=(), derived=(), derive=None, lag=None,
+        fa=None, init=None, device=None):
+    """sde!{ ... drift, diffusion, particles } (pharmsol-macros/src/expand/sde.rs:25-117)."""
+    src = _authoring(name, "sde", params, covariates, states, outputs, routes, derived,
+                     _body(derive=derive, lag=lag, fa=fa, init=init, out=out, dx=drift, noise=diffusion), particles=particles)
+    return Equation.from_dsl(src, device)
+
+
+# ---------------------------------------------------------------------------------------------
+# psi matrix (likelihood/matrix.rs)
+# ---------------------------------------------------------------------------------------------
+def log_likelihood_matrix(equation: Equation, subjects: Data, support_points, error_models: AssayErrorModels, progress: bool = False):
+    """likelihood/matrix.rs:52-106.  `support_points`: rows = support points, cols = parameters in
+    model order.  Returns an F-order (n_subjects, n_support_points) array of log-likelihoods; the
+    first failing pair raises `PharmsolError` (matrix.rs:96-104)."""
+    spp = np.asarray(support_points, dtype=np.float64)
+    if progress:
+        print(f"Computing log-likelihood matrix: {len(subjects)} subjects × {spp.shape[0]} support points...")
+    out = equation.log_likelihood_matrix(subjects, spp, error_models)
+    if progress:
+        ctx = equation._ctx()
+        n = len(subjects) * spp.shape[0]
+        ms = ctx.last_kernel_ms
+        print(f"Progress: {n}/{n} (100%) kernel {ms:.3f} ms, {n / max(ms, 1e-9) * 1e3:.3e} pairs/s")
+    return out
+
+
+def log_psi(equation, subjects, support_points, error_models, progress=False):
+    warnings.warn("Use log_likelihood_matrix() instead", DeprecationWarning)
+    return log_likelihood_matrix(equation, subjects, support_points, error_models, progress)
+
+
+def psi(equation, subjects, support_points, error_models, progress=False):
+    """matrix.rs:138-150: exp of the log-likelihood matrix (exponentiated on the device)."""
+    warnings.warn("Use log_likelihood_matrix() instead and exponentiate if needed", DeprecationWarning)
+    return equation.log_likelihood_matrix(subjects, np.asarray(support_points, dtype=np.float64), error_models, exponentiate=True)
+
+
+class ParameterOrder:
+    """parameter_order.rs: validate an external column order once, then permute support-point
+    matrices into model order."""
+
+    def __init__(self, perm):
+        self.perm = list(perm)
+
+    @classmethod
+    def with_model(cls, equation: Equation, names: Sequence[str]):
+        model_names = equation.parameter_names()
+        names = list(names)
+        if sorted(names) != sorted(model_names):
+            raise PharmsolError(15, f"parameter order {names} does not match model parameters {model_names}")
+        return cls([names.index(n) for n in model_names])
+
+    def matrix(self, support_points):
+        spp = np.asarray(support_points, dtype=np.float64)
+        return np.ascontiguousarray(spp[:, self.perm])

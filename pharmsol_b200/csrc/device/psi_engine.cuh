@@ -1,0 +1,268 @@
+// psi_engine.cuh — the fused psi kernel: one thread per (subject, support point) pair walks the
+// subject's flattened timeline, simulates (closed form or adaptive ODE), evaluates the outputs at
+// every observation, accumulates the log-likelihood and stores psi column-major.
+//
+// Mapping: threadIdx/blockIdx.x run over support points (a warp = 32 consecutive support points of
+// ONE subject, so all lanes walk the same timeline and only parameter-dependent control flow
+// diverges: lag-shifted bolus times and adaptive step counts); blockIdx.y runs over subjects.
+// Support points are SoA (P x nspp) => every parameter load is a coalesced 256-B warp transaction;
+// event / covariate / infusion records are warp-uniform broadcast loads that live in L1.
+//
+// Semantics follow the reference's DSL runtime (the device route for user models):
+//   event loop          dsl/native.rs:1797-1868 (analytical), 1178-1513 (ODE); == the generic loop
+//                       equation/mod.rs:480-516 + simulate_event :300-358 on the reference fixtures
+//   route properties    dsl/native.rs:926-1025   (lag at the bolus time, fa at the lagged time)
+//   initial state       dsl/native.rs:886-924    (derive at t=0, init only on occasion 0)
+//   observations        dsl/native.rs:1044-1086  (derive at t_obs with active route inputs)
+//   analytical interval dsl/native.rs:1871-1937  (== analytical/mod.rs:299-370)
+//   ODE run_events      ode/mod.rs:609-824, closure.rs:103-195 (stop at infusion boundaries,
+//                       restart after bolus / boundary)
+// `M` is the model policy struct emitted by the DSL -> CUDA-C code generator (host/dsl_emit.cpp).
+#pragma once
+#include "psi_analytical.cuh"
+#include "psi_ode.cuh"
+#include "psi_stiff.cuh"
+#include "psi_sde.cuh"
+
+namespace psi {
+
+// ODE right-hand side: derive/covariates refreshed at every call at absolute t (native.rs:1221-1268)
+template <class M>
+struct OdeRhs {
+    PairCtx<M>& c;
+    PSI_DEV void operator()(double t, const double* x, double* dx) {
+        if constexpr (M::RHS_USES_COV) fill_cov<M>(*c.pop, c.occ, t, c.cov);
+        if constexpr (M::HAS_DERIVE && M::DERIVE_DEPS != 0 && M::RHS_USES_DERIVED) M::derive(t, x, c.p, c.cov, c.rate, c.d);
+        M::dynamics(t, x, c.p, c.cov, c.rate, c.d, dx);
+    }
+    PSI_DEV void jacobian(double t, const double* x, double* J) {
+        if constexpr (M::RHS_USES_COV) fill_cov<M>(*c.pop, c.occ, t, c.cov);
+        M::jacobian(t, x, c.p, c.cov, c.rate, J);
+    }
+};
+
+// The solver is a compile-time parameter of the kernel so the explicit kernels do not pay the
+// register cost of the implicit ones (Jacobian + LU) and vice versa.
+template <class M, int SOLVER>
+PSI_DEV int ode_advance(OdeState<M::NSTATE>& st, double tstop, OdeRhs<M>& f, const RunOpts& opt, Counters& cnt) {
+    if constexpr (SOLVER == SOLVER_TSIT5) return erk_integrate_to<Tsit5, M::NSTATE>(st, tstop, f, opt, cnt);
+    else if constexpr (SOLVER == SOLVER_SDIRK4) return sdirk4_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
+    else if constexpr (SOLVER == SOLVER_TRBDF2) return trbdf2_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
+    else return erk_integrate_to<Dopri5, M::NSTATE>(st, tstop, f, opt, cnt);
+}
+
+// One (subject, support point) pair.  Returns the summed log-likelihood; `status` != 0 on error.
+template <class M, int SOLVER>
+PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCtx<M>& c, int& status, Counters& cnt,
+                        double* __restrict__ pred, long long pred_ld) {
+    constexpr int NS = M::NSTATE;
+    constexpr int NR = AtLeast1<M::NROUTE>::v;
+    double ll = 0.0;
+    c.pop = &pop;
+
+    // time-invariant derive is hoisted out of everything (derive reads only parameters/constants)
+    if constexpr (M::HAS_DERIVE && M::DERIVE_DEPS == 0) {
+        double zx[AtLeast1<NS>::v];
+#pragma unroll
+        for (int k = 0; k < AtLeast1<NS>::v; ++k) zx[k] = 0.0;
+        c.zero_rate();
+        M::derive(0.0, zx, c.p, c.cov, c.rate, c.d);
+    } else {
+#pragma unroll
+        for (int k = 0; k < AtLeast1<M::NDER>::v; ++k) c.d[k] = 0.0;
+    }
+
+    // analytical: hoist the kernel coefficients too when nothing they depend on varies
+    [[maybe_unused]] AKernel<(M::KIND == 1 ? M::AKERNEL : 0)> ak;
+    constexpr bool AK_HOISTED = (M::KIND == 1) && (!M::HAS_DERIVE || M::DERIVE_DEPS == 0 || !M::KP_USES_DERIVED);
+    if constexpr (AK_HOISTED) {
+        double kp[8];
+        M::kparams(c.p, c.d, kp);
+        ak.setup_kp(kp, status);
+    }
+
+    const int occ0 = __ldg(pop.occ_offsets + subj), occ1 = __ldg(pop.occ_offsets + subj + 1);
+    for (int occ = occ0; occ < occ1; ++occ) {
+        c.occ = occ;
+        const InfRange inf = occ_infusions(pop, occ);
+
+        // ---- initial state (native.rs:886-924) -------------------------------------------------
+        double x[AtLeast1<NS>::v];
+#pragma unroll
+        for (int k = 0; k < AtLeast1<NS>::v; ++k) x[k] = 0.0;
+        if constexpr (M::HAS_INIT) {
+            if (__ldg(pop.occ_index + occ) == 0) {
+                c.zero_rate();
+                c.refresh(0.0, x);
+                M::init(0.0, x, c.p, c.cov, c.rate, c.d, x);
+            }
+        }
+
+        // ---- event cursor with per-thread lag ---------------------------------------------------
+        auto lag_of = [&](int route, double tb) -> double {
+            if constexpr (M::HAS_LAG) {
+                double zx[AtLeast1<NS>::v];
+#pragma unroll
+                for (int k = 0; k < AtLeast1<NS>::v; ++k) zx[k] = 0.0;
+                c.zero_rate();
+                c.refresh(tb, zx);
+                return M::lag(route, tb, zx, c.p, c.cov, c.rate, c.d);
+            } else {
+                return 0.0;
+            }
+        };
+        EventCursor<M, decltype(lag_of)> cur(pop, occ, lag_of);
+
+        // ---- ODE solver state -------------------------------------------------------------------
+        [[maybe_unused]] OdeState<AtLeast1<NS>::v> st;
+        [[maybe_unused]] OdeRhs<M> rhs{c};
+        [[maybe_unused]] int bnd = 0, bnd_end = 0;
+        if constexpr (M::KIND == 0) {
+            st.t = __ldg(pop.occ_t0 + occ);
+            st.h = -1.0;
+            st.have_k1 = false;
+            bnd = __ldg(pop.bnd_offsets + occ);
+            bnd_end = __ldg(pop.bnd_offsets + occ + 1);
+        }
+
+        EventRec e;
+        double te;
+        bool have = cur.next(e, te);
+        while (have) {
+            const int kind = ev_kind(e.meta);
+            if (kind == EV_BOLUS) {
+                const int route = ev_index(e.meta);
+                double amount = e.a;
+                if constexpr (M::HAS_FA) {                       // native.rs:991-1018, at the lagged time
+                    double zx[AtLeast1<NS>::v];
+#pragma unroll
+                    for (int k = 0; k < AtLeast1<NS>::v; ++k) zx[k] = 0.0;
+                    c.zero_rate();
+                    c.refresh(te, zx);
+                    const double fa = M::fa(route, te, zx, c.p, c.cov, c.rate, c.d);
+                    if (fa != 1.0) amount *= fa;
+                }
+                const int dest = M::bolus_dest(route);           // native.rs:1027-1042
+                if (dest < 0) { if (status == ST_OK) status = ST_UNSUPPORTED_INPUT_ROUTE_KIND; }
+                add_at<AtLeast1<NS>::v>(x, dest, amount);
+                if constexpr (M::KIND == 0) st.have_k1 = false, st.h = -1.0;   // pending_reinit (ode/mod.rs:687)
+            } else if (kind == EV_OBS) {
+                // observation_prediction (native.rs:1044-1086)
+                active_rates<NR>(inf, te, c.rate);
+                c.refresh(te, x);
+                double y[AtLeast1<M::NOUT>::v];
+#pragma unroll
+                for (int k = 0; k < AtLeast1<M::NOUT>::v; ++k) y[k] = 0.0;
+                M::outputs(te, x, c.p, c.cov, c.rate, c.d, y);
+                const double yp = pick<AtLeast1<M::NOUT>::v>(y, ev_index(e.meta));
+                if (pred && e.obs_row >= 0) pred[(long long)e.obs_row * pred_ld] = yp;
+                if (opt.want_ll && ev_has_value(e.meta)) ll += obs_log_likelihood(e, yp, status);
+            }
+            // ---- advance to the next event ------------------------------------------------------
+            EventRec en;
+            double tn;
+            have = cur.next(en, tn);
+            if (have) {
+                if constexpr (M::KIND == 1) {
+                    // Analytical interval (native.rs:1871-1937): split at interior infusion
+                    // boundaries, dedup at 1e-12, derive at the sub-interval end, kernel step.
+                    if (te != tn) {
+                        double last = te;
+                        while (true) {
+                            // smallest candidate c in {boundaries strictly inside (te,tn)} U {tn} with c - last >= 1e-12
+                            double nxt = psi_inf();
+                            for (int i = 0; i < inf.n; ++i) {
+                                double s, dd, a; int input;
+                                load_inf(inf.p + i, s, dd, a, input);
+                                const double f2 = s + dd;
+                                if (s > te && s < tn && s > last && !(fabs(s - last) < 1e-12)) nxt = fmin(nxt, s);
+                                if (f2 > te && f2 < tn && f2 > last && !(fabs(f2 - last) < 1e-12)) nxt = fmin(nxt, f2);
+                            }
+                            if (tn > last && !(fabs(tn - last) < 1e-12)) nxt = fmin(nxt, tn);
+                            if (!(nxt < psi_inf())) break;
+                            const double dt = nxt - last;
+                            interval_rates<NR>(inf, last, nxt, c.rate);
+                            if constexpr (!AK_HOISTED) {
+                                // derive time: sub-interval END (DSL, native.rs:1903-1916) or the
+                                // sub-interval LENGTH (analytical! macro quirk)
+                                c.refresh(opt.cov_time == COVTIME_INTERVAL_LENGTH ? dt : nxt, x);
+                                double kp[8];
+                                M::kparams(c.p, c.d, kp);
+                                ak.setup_kp(kp, status);
+                            }
+                            ak.step(x, dt, c.rate[0]);           // built-in kernels read rateiv[0] only (A.3)
+                            cnt.evals++;
+                            last = nxt;
+                        }
+                    }
+                } else if constexpr (M::KIND == 0) {
+                    // ODE::run_events advance loop (ode/mod.rs:718-819)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) st.y[k] = x[k];
+                    while (tn > st.t) {
+                        while (bnd < bnd_end && __ldg(pop.bnds + bnd) <= st.t) ++bnd;
+                        double stop = tn;
+                        bool is_bnd = false;
+                        if (bnd < bnd_end) {
+                            const double b = __ldg(pop.bnds + bnd);
+                            if (b <= tn) { stop = b; is_bnd = true; ++bnd; }
+                        }
+                        segment_rates<NR>(inf, st.t, c.rate);    // constant on [st.t, stop): right-continuous at
+                                                                 // st.t, left-continuous at stop (closure.rs:43-51)
+                        const int rc = ode_advance<M, SOLVER>(st, stop, rhs, opt, cnt);
+                        if (rc != ST_OK) { if (status == ST_OK) status = rc; st.t = tn; break; }
+                        if (is_bnd) st.have_k1 = false;          // RHS discontinuity: refresh dy (ode/mod.rs:568-586)
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) x[k] = st.y[k];
+                }
+            }
+            e = en;
+            te = tn;
+        }
+    }
+    return ll;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel entry: grid = (ceil(ncols/128), min(nsub, 65535)), block = 128.
+// spp is SoA: spp[k*spp_ld + j]; psi is column-major: out.ll[i + j*out.ld_ll].
+// ---------------------------------------------------------------------------------------------
+template <class M, int SOLVER>
+__device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
+                                                long long spp_ld, const RunOpts& opt, const OutView& out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    Counters cnt;
+    for (int subj = blockIdx.y; subj < pop.nsub; subj += gridDim.y) {
+        PairCtx<M> c;
+#pragma unroll
+        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
+        int status = ST_OK;
+        double* pred = (opt.want_pred && out.pred) ? out.pred + j : nullptr;
+        double ll = run_pair<M, SOLVER>(pop, opt, subj, c, status, cnt, pred, out.ld_pred);
+        if (status != ST_OK) {
+            ll = psi_nan();
+            report_error(out, (long long)subj + j * (long long)pop.nsub, status);
+        }
+        if (out.ll) out.ll[(long long)subj + j * out.ld_ll] = ll;
+    }
+    flush_counters(out, cnt);
+}
+
+template <class M, int SOLVER>
+__device__ __forceinline__ void psi_dispatch(const PopView& pop, const double* __restrict__ spp, long long ncols,
+                                             long long spp_ld, const RunOpts& opt, const OutView& out) {
+    if constexpr (M::KIND == 2) psi_sde_kernel_body<M>(pop, spp, ncols, spp_ld, opt, out);
+    else psi_kernel_body<M, SOLVER>(pop, spp, ncols, spp_ld, opt, out);
+}
+
+}  // namespace psi
+
+// The emitted translation unit instantiates:  PSI_DEFINE_ENTRY(Model, SOLVER, psi_entry_<id>)
+#define PSI_DEFINE_ENTRY(MODEL, SOLVER, NAME)                                                                 \
+    extern "C" __global__ void __launch_bounds__(128)                                                         \
+    NAME(psi::PopView pop, const double* __restrict__ spp, long long ncols, long long spp_ld, psi::RunOpts opt, \
+         psi::OutView out) {                                                                                  \
+        psi::psi_dispatch<MODEL, SOLVER>(pop, spp, ncols, spp_ld, opt, out);                                  \
+    }

@@ -1,0 +1,406 @@
+// abi.cpp — the extern "C" surface declared in include/pharmsol_cuda.h.
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "../../../include/pharmsol_cuda.h"
+#include "runtime.hpp"
+
+using namespace pharmsol;
+
+struct pcu_ctx { Ctx c; };
+struct pcu_model { Model m; };
+struct pcu_subject_builder { SubjectBuilder b; explicit pcu_subject_builder(const char* id) : b(id) {} };
+struct pcu_subject { Subject s; };
+struct pcu_data { Data d; };
+struct pcu_population { Population p; AssayErrorModels em; bool has_em = false; };
+
+namespace {
+
+template <class F>
+int32_t guarded(F&& f) {
+    try {
+        return f();
+    } catch (const PharmsolError& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const dsl::DslError& e) {
+        set_last_error(e.what());
+        return PCU_ERR_COMPILE;
+    } catch (const CudaError& e) {
+        set_last_error(e.what());
+        return PCU_ERR_CUDA;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return PCU_ERR_OTHER;
+    }
+}
+
+AssayErrorModels to_models(const pcu_error_model* ems, int32_t n) {
+    AssayErrorModels out;
+    for (int32_t i = 0; i < n; ++i) {
+        AssayErrorModel m;
+        m.kind = (ErrKind)ems[i].kind;
+        m.factor = ems[i].factor;
+        m.poly = ErrorPoly{ems[i].c0, ems[i].c1, ems[i].c2, ems[i].c3};
+        out.models.push_back(m);
+    }
+    return out;
+}
+
+cudaStream_t pick_stream(Ctx& c, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : c.stream; }
+
+int32_t collect(Ctx& c, int32_t* code, int64_t* pair) {
+    unsigned long long host[5];
+    cuda_check(cudaMemcpy(host, c.err_ctr.p, sizeof host, cudaMemcpyDeviceToHost), "read error word");
+    for (int k = 0; k < 4; ++k) c.last_counters[k] = host[1 + k];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_kernel_ms = ms;
+    if (host[0] == ~0ull) {
+        if (code) *code = 0;
+        if (pair) *pair = -1;
+        return PCU_OK;
+    }
+    const int32_t ec = (int32_t)(host[0] & 0xff);
+    // device pair index = i + j_local*nsub; make it global with the shard's first column
+    const int64_t local = (int64_t)(host[0] >> 8);
+    const int64_t gp = local + c.pending_first_col * c.pending_nsub;
+    if (code) *code = ec;
+    if (pair) *pair = gp;
+    set_last_error("psi evaluation failed for pair " + std::to_string(gp) + " with status " + std::to_string(ec));
+    return ec;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pharmsol_cuda_abi_version(void) { return PHARMSOL_CUDA_ABI_VERSION; }
+
+int32_t pharmsol_cuda_device_count(int32_t* n) {
+    return guarded([&] {
+        int c = 0;
+        cuda_check(cudaGetDeviceCount(&c), "cudaGetDeviceCount");
+        if (n) *n = c;
+        return PCU_OK;
+    });
+}
+
+int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
+    return guarded([&] {
+        if (!out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        cuda_check(cudaSetDevice(device), "cudaSetDevice");
+        cudaDeviceProp prop;
+        cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+        if (prop.major < 10) throw CudaError(std::string("device `") + prop.name + "` is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this backend is built for sm_100a only");
+        auto* c = new pcu_ctx();
+        c->c.device = device;
+        c->c.sm_count = prop.multiProcessorCount;
+        cuda_check(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cuda_check(cudaEventCreate(&c->c.ev0), "cudaEventCreate");
+        cuda_check(cudaEventCreate(&c->c.ev1), "cudaEventCreate");
+        c->c.err_ctr.reserve(5 * sizeof(unsigned long long));
+        *out = c;
+        return (int32_t)PCU_OK;
+    });
+}
+void pharmsol_cuda_ctx_destroy(pcu_ctx* ctx) { delete ctx; }
+const char* pharmsol_cuda_last_error_message(void) { return last_error().c_str(); }
+int64_t pharmsol_cuda_launch_count(pcu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+double pharmsol_cuda_last_kernel_ms(pcu_ctx* ctx) { return ctx ? ctx->c.last_kernel_ms : 0.0; }
+int32_t pharmsol_cuda_last_counters(pcu_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return PCU_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < 4; ++k) out[k] = ctx->c.last_counters[k];
+    return PCU_OK;
+}
+int32_t pharmsol_cuda_host_alloc(size_t bytes, void** out) {
+    return guarded([&] { cuda_check(cudaMallocHost(out, bytes), "cudaMallocHost"); return PCU_OK; });
+}
+int32_t pharmsol_cuda_host_free(void* p) {
+    return guarded([&] { cuda_check(cudaFreeHost(p), "cudaFreeHost"); return PCU_OK; });
+}
+
+// ---- data ------------------------------------------------------------------------------------------------
+pcu_subject_builder* pharmsol_subject_builder_new(const char* id) { return new pcu_subject_builder(id ? id : ""); }
+void pharmsol_subject_builder_bolus(pcu_subject_builder* b, double t, double a, const char* input) { b->b.bolus(t, a, input); }
+void pharmsol_subject_builder_infusion(pcu_subject_builder* b, double t, double a, const char* input, double dur) { b->b.infusion(t, a, input, dur); }
+void pharmsol_subject_builder_observation(pcu_subject_builder* b, double t, double v, const char* outeq) { b->b.observation(t, v, outeq); }
+void pharmsol_subject_builder_censored_observation(pcu_subject_builder* b, double t, double v, const char* outeq, int32_t cens) {
+    b->b.censored_observation(t, v, outeq, (Censor)cens);
+}
+void pharmsol_subject_builder_missing_observation(pcu_subject_builder* b, double t, const char* outeq) { b->b.missing_observation(t, outeq); }
+void pharmsol_subject_builder_observation_with_error(pcu_subject_builder* b, double t, double v, const char* outeq, double c0, double c1,
+                                                     double c2, double c3, int32_t cens) {
+    b->b.observation_with_error(t, v, outeq, ErrorPoly{c0, c1, c2, c3}, (Censor)cens);
+}
+void pharmsol_subject_builder_covariate(pcu_subject_builder* b, const char* name, double t, double v) { b->b.covariate(name, t, v); }
+void pharmsol_subject_builder_repeat(pcu_subject_builder* b, int64_t n, double delta) { b->b.repeat((size_t)n, delta); }
+void pharmsol_subject_builder_reset(pcu_subject_builder* b) { b->b.reset(); }
+pcu_subject* pharmsol_subject_builder_build(pcu_subject_builder* b) {
+    auto* s = new pcu_subject{b->b.build()};
+    delete b;
+    return s;
+}
+int32_t pharmsol_subject_set_covariate_fixed(pcu_subject* s, int32_t occasion, const char* name, int32_t fixed) {
+    if (!s || occasion < 0 || (size_t)occasion >= s->s.occasions.size()) return PCU_ERR_INVALID_ARGUMENT;
+    auto& covs = s->s.occasions[(size_t)occasion].covariates;
+    auto it = covs.find(name);
+    if (it == covs.end()) return PCU_ERR_MISSING_COVARIATE;
+    it->second.fixed = fixed != 0;
+    return PCU_OK;
+}
+void pharmsol_subject_free(pcu_subject* s) { delete s; }
+pcu_data* pharmsol_data_new(void) { return new pcu_data(); }
+int32_t pharmsol_data_add_subject(pcu_data* d, const pcu_subject* s) {
+    if (!d || !s) return PCU_ERR_INVALID_ARGUMENT;
+    d->d.subjects.push_back(s->s);
+    return PCU_OK;
+}
+int64_t pharmsol_data_len(const pcu_data* d) { return d ? (int64_t)d->d.subjects.size() : 0; }
+void pharmsol_data_free(pcu_data* d) { delete d; }
+
+// ---- models ----------------------------------------------------------------------------------------------
+int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, pcu_model** out) {
+    return guarded([&] {
+        if (!source || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        auto* m = new pcu_model();
+        try {
+            m->m.cm = dsl::compile_source(std::string(source, len));
+        } catch (...) { delete m; throw; }
+        std::memset(&m->m.opts, 0, sizeof m->m.opts);
+        m->m.opts.rtol = 1e-4; m->m.opts.atol = 1e-4;            // ode/mod.rs:40-41
+        m->m.opts.h0 = 0.0;
+        m->m.opts.em_dt = 0.05;
+        m->m.opts.seed = 0x5eed5eedULL;
+        m->m.opts.solver = psi::SOLVER_DOPRI5;
+        m->m.opts.cov_time = psi::COVTIME_INTERVAL_END;
+        m->m.opts.max_steps = 200000;
+        m->m.opts.nparticles = m->m.cm.particles > 0 ? m->m.cm.particles : 1000;
+        m->m.opts.sde_mode = psi::SDE_MEAN_PREDICTION;
+        m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;
+        m->m.info_json = m->m.cm.model_info_json();
+        std::vector<std::pair<int, std::string>> entries;
+        if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 4; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
+        else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
+        m->m.source_cache = m->m.cm.cuda_source(entries, false);
+        *out = m;
+        return (int32_t)PCU_OK;
+    });
+}
+void pharmsol_cuda_model_destroy(pcu_model* m) { delete m; }
+int32_t pharmsol_cuda_model_kind(const pcu_model* m) { return (int32_t)m->m.cm.kind; }
+int32_t pharmsol_cuda_model_nparams(const pcu_model* m) { return (int32_t)m->m.cm.parameters.size(); }
+int32_t pharmsol_cuda_model_nstates(const pcu_model* m) { return m->m.cm.state_len; }
+int32_t pharmsol_cuda_model_nouteqs(const pcu_model* m) { return m->m.cm.output_len; }
+const char* pharmsol_cuda_model_info_json(const pcu_model* m) { return m->m.info_json.c_str(); }
+const char* pharmsol_cuda_model_cuda_source(const pcu_model* m) { return m->m.source_cache.c_str(); }
+const char* pharmsol_cuda_model_id(const pcu_model* m) { return m->m.cm.id.c_str(); }
+int32_t pharmsol_cuda_model_set_solver(pcu_model* m, int32_t solver, double rtol, double atol) {
+    if (!m || solver < 0 || solver > 3 || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
+    m->m.opts.solver = solver; m->m.opts.rtol = rtol; m->m.opts.atol = atol;
+    return PCU_OK;
+}
+int32_t pharmsol_cuda_model_set_max_steps(pcu_model* m, int32_t n) {
+    if (!m || n <= 0) return PCU_ERR_INVALID_ARGUMENT;
+    m->m.opts.max_steps = n;
+    return PCU_OK;
+}
+int32_t pharmsol_cuda_model_set_particles(pcu_model* m, uint32_t n, uint64_t seed, int32_t sde_mode, int32_t em_mode, double em_dt) {
+    if (!m || n == 0 || sde_mode < 0 || sde_mode > 1 || em_mode < 0 || em_mode > 1) return PCU_ERR_INVALID_ARGUMENT;
+    m->m.opts.nparticles = (int32_t)n; m->m.opts.seed = seed; m->m.opts.sde_mode = sde_mode; m->m.opts.em_mode = em_mode;
+    if (em_dt > 0) m->m.opts.em_dt = em_dt;
+    return PCU_OK;
+}
+int32_t pharmsol_cuda_model_set_cov_time(pcu_model* m, int32_t mode) {
+    if (!m || mode < 0 || mode > 1) return PCU_ERR_INVALID_ARGUMENT;
+    m->m.opts.cov_time = mode;
+    return PCU_OK;
+}
+int32_t pharmsol_cuda_model_compile(pcu_ctx* ctx, pcu_model* m, int32_t* source_out) {
+    return guarded([&] {
+        if (!ctx || !m) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        KernelRef k = get_kernel(m->m, effective_solver(m->m));
+        if (source_out) *source_out = k.source;
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_model_precompile_to_cache(pcu_model* m, int32_t solver) {
+    return guarded([&] {
+        if (!m) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        const std::string name = entry_name(m->m.cm.id, solver);
+        auto cubin = nvrtc_compile_cubin(m->m.cm.cuda_source({{solver, name}}, false), name);
+        const std::string path = cubin_cache_path(m->m.cm.id, solver);
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) throw PharmsolError(PCU_ERR_OTHER, "cannot write " + path);
+        std::fwrite(cubin.data(), 1, cubin.size(), f);
+        std::fclose(f);
+        return (int32_t)PCU_OK;
+    });
+}
+
+// ---- population --------------------------------------------------------------------------------------------
+int32_t pharmsol_cuda_population_create(pcu_ctx* ctx, const pcu_model* m, const pcu_data* d, const pcu_error_model* ems,
+                                        int32_t n_ems, pcu_population** out) {
+    return guarded([&] {
+        if (!ctx || !m || !d || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        auto* p = new pcu_population();
+        try {
+            p->p.data = d->d;
+            p->p.labels = m->m.cm.labels();
+            p->p.device = ctx->c.device;
+            if (ems && n_ems > 0) { p->em = to_models(ems, n_ems); p->has_em = true; }
+            p->p.flat = flatten_population(p->p.data, p->p.labels, p->has_em ? &p->em : nullptr);
+            p->p.upload();
+        } catch (...) { delete p; throw; }
+        *out = p;
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_population_set_error_models(pcu_population* pop, const pcu_error_model* ems, int32_t n) {
+    return guarded([&] {
+        if (!pop) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        cuda_check(cudaSetDevice(pop->p.device), "cudaSetDevice");
+        pop->has_em = ems && n > 0;
+        if (pop->has_em) pop->em = to_models(ems, n);
+        pop->p.flat = flatten_population(pop->p.data, pop->p.labels, pop->has_em ? &pop->em : nullptr);
+        pop->p.upload();
+        return (int32_t)PCU_OK;
+    });
+}
+void pharmsol_cuda_population_destroy(pcu_population* pop) {
+    if (!pop) return;
+    pop->p.dev.release();
+    delete pop;
+}
+int64_t pharmsol_cuda_population_nsubjects(const pcu_population* pop) { return pop ? pop->p.flat.nsub : 0; }
+int64_t pharmsol_cuda_population_nobservations(const pcu_population* pop) { return pop ? pop->p.flat.nobs_total : 0; }
+int32_t pharmsol_cuda_population_obs_offsets(const pcu_population* pop, int64_t* out) {
+    if (!pop || !out) return PCU_ERR_INVALID_ARGUMENT;
+    for (size_t i = 0; i < pop->p.flat.obs_offsets.size(); ++i) out[i] = pop->p.flat.obs_offsets[i];
+    return PCU_OK;
+}
+int64_t pharmsol_cuda_population_device_bytes(const pcu_population* pop) { return pop ? (int64_t)pop->p.dev.cap : 0; }
+
+// ---- hot path ------------------------------------------------------------------------------------------------
+int32_t pharmsol_cuda_upload_support_points(pcu_ctx* ctx, const double* spp, int64_t nspp, int32_t np, double* spp_soa_dev,
+                                            int64_t ld, void* stream) {
+    return guarded([&] {
+        if (!ctx || !spp || !spp_soa_dev || nspp < 0 || np <= 0 || ld < nspp) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        cudaStream_t s = pick_stream(ctx->c, stream);
+        ctx->c.spp_rows.reserve((size_t)nspp * np * 8);
+        cuda_check(cudaMemcpyAsync(ctx->c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, s), "H2D support points");
+        launch_transpose(ctx->c.spp_rows.as<double>(), spp_soa_dev, nspp, np, ld, s);
+        ctx->c.launches += 1;
+        return (int32_t)PCU_OK;
+    });
+}
+
+int32_t pharmsol_cuda_log_likelihood_matrix_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev,
+                                                   int64_t ncols, int64_t ld_spp, double* out_dev, int64_t ld_out,
+                                                   int64_t first_col, void* stream) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp_soa_dev || !out_dev || ld_out < pop->p.flat.nsub) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        launch_psi(ctx->c, m->m, pop->p, spp_soa_dev, ncols, ld_spp, out_dev, ld_out, nullptr, 0, first_col, pick_stream(ctx->c, stream));
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev, int64_t ncols,
+                                         int64_t ld_spp, double* pred_dev, int64_t ld_pred, double* ll_dev, int64_t ld_out, void* stream) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp_soa_dev || !pred_dev) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        launch_psi(ctx->c, m->m, pop->p, spp_soa_dev, ncols, ld_spp, ll_dev, ld_out, pred_dev, ld_pred, 0, pick_stream(ctx->c, stream));
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* code, int64_t* pair) {
+    return guarded([&] {
+        if (!ctx) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        cuda_check(cudaDeviceSynchronize(), "synchronize");
+        return collect(ctx->c, code, pair);
+    });
+}
+
+static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp, int32_t np,
+                           double* out, int32_t* code, int64_t* pair, bool exponentiate) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp || !out || nspp < 0) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        if (np != (int32_t)m->m.cm.parameters.size()) {
+            // dsl/native.rs:688-698 validate_support_point
+            throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
+                                                   " parameter value(s), got " + std::to_string(np));
+        }
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        Ctx& c = ctx->c;
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        const int64_t nsub = pop->p.flat.nsub;
+        if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
+        c.spp_rows.reserve((size_t)nspp * np * 8);
+        c.spp_soa.reserve((size_t)nspp * np * 8);
+        c.out.reserve((size_t)nsub * nspp * 8);
+        cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+        launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
+        c.launches += 1;
+        launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, c.out.as<double>(), nsub, nullptr, 0, 0, c.stream);
+        if (exponentiate) { launch_exp_inplace(c.out.as<double>(), nsub * nspp, c.stream); c.launches += 1; }
+        cuda_check(cudaMemcpyAsync(out, c.out.p, (size_t)nsub * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H psi");
+        cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+        return collect(c, code, pair);
+    });
+}
+
+int32_t pharmsol_cuda_log_likelihood_matrix(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp,
+                                            int32_t np, double* out, int32_t* code, int64_t* pair) {
+    return matrix_host(ctx, m, pop, spp, nspp, np, out, code, pair, false);
+}
+int32_t pharmsol_cuda_psi(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp, int32_t np, double* out,
+                          int32_t* code, int64_t* pair) {
+    return matrix_host(ctx, m, pop, spp, nspp, np, out, code, pair, true);
+}
+
+int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp, int32_t np, double* out) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp || !out || nspp < 0) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        if (np != (int32_t)m->m.cm.parameters.size())
+            throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
+                                                   " parameter value(s), got " + std::to_string(np));
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        Ctx& c = ctx->c;
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        const int64_t nobs = pop->p.flat.nobs_total;
+        if (nspp == 0 || nobs == 0) return (int32_t)PCU_OK;
+        c.spp_rows.reserve((size_t)nspp * np * 8);
+        c.spp_soa.reserve((size_t)nspp * np * 8);
+        c.pred.reserve((size_t)nobs * nspp * 8);
+        cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+        launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
+        c.launches += 1;
+        // predictions need no error model: run with the likelihood output disabled
+        launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, nullptr, pop->p.flat.nsub, c.pred.as<double>(), nspp, 0, c.stream);
+        cuda_check(cudaMemcpyAsync(out, c.pred.p, (size_t)nobs * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H predictions");
+        cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+        int32_t code = 0; int64_t pair = -1;
+        return collect(c, &code, &pair);
+    });
+}
+
+int32_t pharmsol_cuda_measure_fp64_peak(pcu_ctx* ctx, double* tflops, double* clock_mhz) {
+    return guarded([&] {
+        if (!ctx || !tflops) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        *tflops = measure_fp64_peak(ctx->c, clock_mhz);
+        return (int32_t)PCU_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// runtime.hpp — context / model / population objects behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "data.hpp"
+#include "dsl.hpp"
+
+namespace pharmsol {
+
+void set_last_error(const std::string& msg);
+const std::string& last_error();
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& m) : std::runtime_error(m) {}
+};
+void cuda_check(cudaError_t e, const char* what);
+
+// A grow-only device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes);
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+enum KernelSource : int { SRC_AOT = 0, SRC_CACHE = 1, SRC_NVRTC = 2 };
+struct KernelRef {
+    const void* fn = nullptr;      // function pointer (AOT) or cudaKernel_t (runtime-loaded library)
+    int source = SRC_AOT;
+    std::string name;
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
+    DevBuf spp_rows, spp_soa, out, pred, scratch;
+    int64_t launches = 0;
+    double last_kernel_ms = 0.0;
+    unsigned long long last_counters[4] = {0, 0, 0, 0};
+    int64_t pending_nsub = 0, pending_first_col = 0;
+    ~Ctx();
+};
+
+struct Model {
+    dsl::CompiledModel cm;
+    psi::RunOpts opts;
+    std::string source_cache;                 // generated CUDA C (for inspection)
+    std::string info_json;
+    std::map<int, KernelRef> kernels;         // by solver id
+    std::mutex mu;
+};
+
+struct Population {
+    Data data;
+    ModelLabels labels;
+    FlatPopulation flat;
+    DevBuf dev;
+    psi::PopView view{};
+    int device = 0;
+    void upload();
+};
+
+// --- module management --------------------------------------------------------------------------------
+// Look up / build the kernel for (model, solver): AOT registry -> cubin cache -> NVRTC.
+KernelRef get_kernel(Model& m, int solver);
+// NVRTC compile to cubin (no device needed); throws dsl::DslError with the compile log on failure.
+std::vector<char> nvrtc_compile_cubin(const std::string& source, const std::string& name);
+std::string cubin_cache_path(const std::string& id, int solver);
+std::string entry_name(const std::string& id, int solver);
+int effective_solver(const Model& m);
+
+// --- launches -------------------------------------------------------------------------------------------
+void launch_psi(Ctx& ctx, Model& m, Population& pop, const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                double* out_dev, int64_t ld_out, double* pred_dev, int64_t ld_pred, int64_t first_col, cudaStream_t stream);
+void launch_transpose(const double* rows, double* soa, int64_t nspp, int nparams, int64_t ld, cudaStream_t stream);
+void launch_exp_inplace(double* p, int64_t n, cudaStream_t stream);
+double measure_fp64_peak(Ctx& ctx, double* clock_mhz);
+
+}  // namespace pharmsol
