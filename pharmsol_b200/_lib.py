@@ -383,3 +383,38 @@ def predictions(ctx, model, pop, support_points):
     out = np.empty((pop.nobservations, nspp), dtype=np.float64)
     check(lib().pharmsol_cuda_predictions(ctx.ptr, model.ptr, pop.ptr, _dp(spp), nspp, npar, _dp(out)))
     return out
+
+
+# ---- device-resident entry points (raw device pointers; the caller owns the memory) ---------------
+def upload_support_points(ctx, support_points, spp_soa_ptr, ld_spp, stream=0):
+    """Row-major host (nspp, P) -> parameter-major SoA device buffer spp[k*ld_spp + j]."""
+    spp = np.ascontiguousarray(support_points, dtype=np.float64)
+    nspp, npar = spp.shape
+    check(lib().pharmsol_cuda_upload_support_points(ctx.ptr, _dp(spp), nspp, npar, C.c_void_p(int(spp_soa_ptr)), int(ld_spp),
+                                                    C.c_void_p(int(stream) or None)))
+
+
+def log_likelihood_matrix_device(ctx, model, pop, spp_soa_ptr, ncols, ld_spp, out_ptr, ld_out, first_col=0, stream=0):
+    """Asynchronous launch with everything resident in HBM: out[i + j*ld_out] for j < ncols."""
+    check(lib().pharmsol_cuda_log_likelihood_matrix_device(ctx.ptr, model.ptr, pop.ptr, C.c_void_p(int(spp_soa_ptr)), int(ncols),
+                                                           int(ld_spp), C.c_void_p(int(out_ptr)), int(ld_out), int(first_col),
+                                                           C.c_void_p(int(stream) or None)))
+
+
+def host_alloc(nbytes):
+    p = C.c_void_p()
+    check(lib().pharmsol_cuda_host_alloc(int(nbytes), C.byref(p)))
+    return p.value
+
+
+def host_free(ptr):
+    check(lib().pharmsol_cuda_host_free(C.c_void_p(int(ptr))))
+
+
+def pinned_array(shape, order="C"):
+    """numpy float64 array backed by page-locked host memory (cudaMallocHost through the C ABI)."""
+    n = int(np.prod(shape))
+    ptr = host_alloc(max(n, 1) * 8)
+    buf = (C.c_double * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
+    return arr, ptr

@@ -303,9 +303,9 @@ class Equation:
             return pop
         return pop[0]
 
-    def log_likelihood_matrix(self, data, support_points, error_models, exponentiate=False):
+    def log_likelihood_matrix(self, data, support_points, error_models, exponentiate=False, out=None):
         pop = self.population(data, error_models)
-        return _lib.log_likelihood_matrix(self._ctx(), self._model, pop, support_points, exponentiate=exponentiate)
+        return _lib.log_likelihood_matrix(self._ctx(), self._model, pop, support_points, out=out, exponentiate=exponentiate)
 
     def predictions_matrix(self, data, support_points):
         """(nobs_total, nspp) predictions + per-subject row offsets."""
@@ -505,3 +505,92 @@ class ParameterOrder:
     def matrix(self, support_points):
         spp = np.asarray(support_points, dtype=np.float64)
         return np.ascontiguousarray(spp[:, self.perm])
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident psi (inputs and outputs stay in HBM; optional column sharding over ranks)
+# ---------------------------------------------------------------------------------------------
+class ResidentPsi:
+    """psi with everything resident in HBM: the support points are uploaded once (SoA, P x ncols) and
+    every ``launch()`` is one asynchronous kernel launch on the caller's current CUDA stream writing
+    the column-major block psi[:, first_col : first_col + ncols].
+
+    With ``torch.distributed`` initialised (one process per GPU) the support-point columns are
+    sharded over the ranks (``pharmsol_b200.sharding``) and ``step()`` = launch + in-place all-gather.
+    torch is used for device memory, streams and the process group only.
+    """
+
+    def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True):
+        import torch
+        import torch.distributed as dist
+        from .sharding import ShardedPsi
+        self.torch = torch
+        self.eq = equation
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        equation.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.ctx = equation._ctx()
+        self.pop = equation.population(data, error_models)
+        spp = np.ascontiguousarray(support_points, dtype=np.float64)
+        self.nspp, self.nparams = spp.shape
+        self.nsub = self.pop.nsubjects
+        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device) if (shard and dist.is_available() and dist.is_initialized()) \
+            else _SingleRank(self.nsub, self.nspp, self.device)
+        lo, hi = self.sharded.local_range
+        self.first_col, self.ncols = lo, hi - lo
+        self.ld_spp = max(self.ncols, 1)
+        self.spp_soa = torch.empty((self.nparams, self.ld_spp), dtype=torch.float64, device=self.device)
+        if self.ncols:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.upload_support_points(self.ctx, spp[lo:hi], self.spp_soa.data_ptr(), self.ld_spp, stream)
+            torch.cuda.current_stream(self.device).synchronize()
+        equation._model.compile(self.ctx)
+
+    def launch(self):
+        """One asynchronous psi kernel launch for this rank's columns (no copies, no sync)."""
+        if not self.ncols:
+            return
+        slab = self.sharded.local_slab()
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        _lib.log_likelihood_matrix_device(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,
+                                          slab.data_ptr(), self.nsub, self.first_col, stream)
+
+    def step(self):
+        """launch + all-gather of the column slabs (no-op on one rank); asynchronous."""
+        self.launch()
+        self.sharded.gather()
+
+    def finish(self):
+        """Synchronise, raise the first error over all ranks (matrix.rs:96-104), return psi as a
+        (nsub, nspp) column-major device tensor view."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+        code, pair = 0, -1
+        try:
+            self.ctx.collect_errors()
+        except PharmsolError as e:
+            code, pair = e.code, (e.pair if e.pair is not None else -1)
+        code, pair = self.sharded.reduce_error(code, pair)
+        if code:
+            raise PharmsolError(code, f"psi evaluation failed for pair {pair}", pair)
+        return self.sharded.matrix()
+
+
+class _SingleRank:
+    def __init__(self, nsub, nspp, device):
+        import torch
+        self.world, self.rank, self.nsub, self.nspp = 1, 0, nsub, nspp
+        self.full = torch.empty((nspp, nsub), dtype=torch.float64, device=device)
+        self.local_range = (0, nspp)
+
+    def local_slab(self):
+        return self.full
+
+    def gather(self):
+        return self.full
+
+    def reduce_error(self, code, pair):
+        return code, pair
+
+    def matrix(self):
+        return self.full.t()

@@ -106,6 +106,7 @@ struct RouteInfo {
     RouteKind kind = RouteKind::Bolus;
     int index = 0;            // dense input slot
     int destination = -1;     // destination state offset
+    bool has_lag = false, has_bioavailability = false;   // dsl/model_info.rs route properties
 };
 struct ModelLabels {
     std::vector<RouteInfo> routes;

@@ -380,6 +380,14 @@ void collect_targets(const std::vector<Stmt>& ss, std::vector<std::string>& out)
         else if (s.kind == Stmt::For) collect_targets(s.body, out);
     }
 }
+// names of the states touched by `ddt(state) = ...` statements anywhere in a block
+void collect_state_targets(const std::vector<Stmt>& ss, std::vector<std::string>& out) {
+    for (const auto& s : ss) {
+        if (s.kind == Stmt::Assign && s.callee == "ddt") out.push_back(s.target);
+        else if (s.kind == Stmt::If) { collect_state_targets(s.then_body, out); collect_state_targets(s.else_body, out); }
+        else if (s.kind == Stmt::For) collect_state_targets(s.body, out);
+    }
+}
 void collect_lets(const std::vector<Stmt>& ss, std::vector<std::string>& out) {
     for (const auto& s : ss) {
         if (s.kind == Stmt::Let) { bool seen = false; for (auto& o : out) if (o == s.target) seen = true; if (!seen) out.push_back(s.target); }
@@ -576,7 +584,7 @@ CompiledModel compile_model(const ModelAst& ast_in) {
             r.dest_offset = si->second.offset + (int)ix;
             if (r.has_kind && r.kind == RouteKind::Infusion && (r.lag || r.fa)) throw DslError("lag and bioavailability are bolus-only route properties (route `" + r.name + "`)");
             maxslot = std::max(maxslot, r.index);
-            RouteInfo ri; ri.name = r.name; ri.has_kind = r.has_kind; ri.kind = r.kind; ri.index = r.index; ri.destination = r.dest_offset;
+            RouteInfo ri; ri.name = r.name; ri.has_kind = r.has_kind; ri.kind = r.kind; ri.index = r.index; ri.destination = r.dest_offset; ri.has_lag = (bool)r.lag; ri.has_bioavailability = (bool)r.fa;
             cm.routes.push_back(ri);
             if (r.lag) cm.has_lag = true;
             if (r.fa) cm.has_fa = true;
@@ -641,7 +649,14 @@ CompiledModel compile_model(const ModelAst& ast_in) {
                 S << "        out[" << r.dest_offset << "] += rate[" << r.index << "];   // infusion(" << r.name << ") -> state " << r.dest_offset << "\n";
         }
         S << "    }\n";
-        // every state must be assigned (analyze.rs:2414-2432)
+        // every state must be touched by the block (validate_state_coverage, analyze.rs:2414-2432)
+        std::vector<std::string> touched;
+        collect_state_targets(ast.dynamics, touched);
+        for (const auto& st : ast.states) {
+            bool ok = false;
+            for (const auto& t : touched) ok = ok || t == st.name;
+            if (!ok) throw DslError(std::string(ast.kind == ModelKind::Sde ? "drift" : "dynamics") + " block does not assign `" + st.name + "`");
+        }
     }
     // diffusion
     Scope sc_diff;
@@ -773,7 +788,8 @@ std::string CompiledModel::model_info_json() const {
     for (size_t i = 0; i < routes.size(); ++i) {
         const auto& r = routes[i];
         o << (i ? ", " : "") << "{\"name\": \"" << r.name << "\", \"kind\": " << (r.has_kind ? (r.kind == RouteKind::Bolus ? "\"bolus\"" : "\"infusion\"") : "null")
-          << ", \"index\": " << r.index << ", \"destination_offset\": " << r.destination << "}";
+          << ", \"index\": " << r.index << ", \"destination_offset\": " << r.destination << ", \"has_lag\": " << (r.has_lag ? "true" : "false")
+          << ", \"has_bioavailability\": " << (r.has_bioavailability ? "true" : "false") << "}";
     }
     o << "], \"state_len\": " << state_len << ", \"derived_len\": " << derived_len << ", \"output_len\": " << output_len << ", \"route_len\": " << route_len
       << ", \"analytical\": " << (analytical_kernel >= 0 ? std::string("\"") + kKernelNames[analytical_kernel] + "\"" : "null")

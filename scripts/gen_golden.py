@@ -1,0 +1,130 @@
+"""Generate the committed golden vectors under tests/golden/ from INDEPENDENT mathematics
+(no oracle, no product):
+
+  kernels.json     one-step closed-form kernels vs scipy.linalg.expm of the augmented generator
+                   [[A, b], [0, 0]] (exact for linear systems with constant input)
+  timelines.json   the reference's analytical unit-test fixtures (analytical/mod.rs:446-487 with the
+                   parameters of each *_models.rs test) propagated event-by-event with expm
+  stiff_c4.json    Michaelis-Menten + effect compartment predictions from SciPy Radau, rtol=1e-12
+  normal.json      log-pdf / log-cdf / log-sf anchors from mpmath (50 digits)
+
+Run:  python scripts/gen_golden.py     (deterministic; needs numpy, scipy, mpmath)
+"""
+import json
+import os
+
+import mpmath as mp
+import numpy as np
+from scipy.integrate import solve_ivp
+from scipy.linalg import expm
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+rng = np.random.Generator(np.random.Philox(key=[20261018, 99]))
+
+
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
+from golden_math import generator, step  # noqa: E402
+
+NPAR = {"one_compartment": 1, "one_compartment_with_absorption": 2, "two_compartments": 3, "two_compartments_with_absorption": 4,
+        "three_compartments": 5, "three_compartments_with_absorption": 6}
+
+# ---- kernels.json ---------------------------------------------------------------------------------
+cases = []
+for kernel, npar in NPAR.items():
+    for _ in range(40):
+        p = (0.05 + 2.0 * rng.random(npar)).tolist()
+        n = generator(kernel, p)[0].shape[0]
+        x = (100.0 * rng.random(n)).tolist()
+        dt = float(rng.choice([0.25, 0.5, 1.0, 2.5, 6.0, 12.0]))
+        rate = float(rng.choice([0.0, 0.0, 5.0, 50.0]))
+        cases.append(dict(kernel=kernel, p=p, x=x, dt=dt, rate=rate, out=step(kernel, p, np.array(x), dt, rate).tolist()))
+json.dump(cases, open(os.path.join(OUT, "kernels.json"), "w"), indent=0)
+
+# ---- timelines.json: fixtures of analytical/mod.rs:446-487 -------------------------------------------
+INFUSION_DOSING = dict(
+    ops=[("bolus", 0.0, 100.0, "0"), ("infusion", 24.0, 150.0, "0", 3.0)] +
+        [("missing_observation", t, "0") for t in [0, 1, 2, 4, 8, 12, 24, 25, 26, 27, 28, 32, 36]])
+ORAL_INFUSION = dict(
+    ops=[("bolus", 0.0, 100.0, "1"), ("infusion", 24.0, 150.0, "0", 3.0), ("bolus", 48.0, 100.0, "0")] +
+        [("missing_observation", t, "0") for t in [0, 1, 2, 4, 8, 12, 24, 25, 26, 27, 28, 32, 36, 48, 49, 50, 52, 56, 60]])
+
+
+def simulate(kernel, kp, v, out_state, ops):
+    """Independent event loop: observations before doses at equal times; bolus to state[input];
+    infusion rate feeds the kernel's input compartment; expm between consecutive breakpoints."""
+    n = generator(kernel, kp)[0].shape[0]
+    ev = []
+    for k, op in enumerate(ops):
+        rank = {"missing_observation": 0, "bolus": 1, "infusion": 2}[op[0]]
+        ev.append((op[1], rank, k, op))
+    ev.sort(key=lambda e: (e[0], e[1], e[2]))
+    infs = [(op[1], op[1] + op[4], op[2] / op[4]) for op in ops if op[0] == "infusion"]
+    x = np.zeros(n)
+    preds = []
+    for i, (t, rank, _, op) in enumerate(ev):
+        if op[0] == "bolus":
+            x[int(op[3])] += op[2]
+        elif op[0] == "missing_observation":
+            preds.append(x[out_state] / v)
+        if i + 1 < len(ev):
+            tn = ev[i + 1][0]
+            bps = sorted({t, tn} | {b for s, e, _ in infs for b in (s, e) if t < b < tn})
+            for a, b in zip(bps[:-1], bps[1:]):
+                rate = sum(r for s, e, r in infs if a >= s and b <= e)
+                x = step(kernel, kp, x, b - a, rate)
+    return preds
+
+
+timelines = []
+for kernel, params, kp, v, out_state, fixture in [
+    ("one_compartment", [0.1, 1.0], [0.1], 1.0, 0, INFUSION_DOSING),
+    ("two_compartments", [0.1, 3.0, 1.0, 1.0], [0.1, 3.0, 1.0], 1.0, 0, INFUSION_DOSING),
+    ("three_compartments", [0.1, 3.0, 2.0, 1.0, 0.5, 1.0], [0.1, 3.0, 2.0, 1.0, 0.5], 1.0, 0, INFUSION_DOSING),
+    ("one_compartment_with_absorption", [1.0, 0.1, 1.0], [1.0, 0.1], 1.0, 1, ORAL_INFUSION),
+    ("two_compartments_with_absorption", [0.1, 1.0, 3.0, 1.0, 1.0], [0.1, 1.0, 3.0, 1.0], 1.0, 1, ORAL_INFUSION),
+    ("three_compartments_with_absorption", [1.0, 0.1, 3.0, 2.0, 1.0, 0.5, 1.0], [1.0, 0.1, 3.0, 2.0, 1.0, 0.5], 1.0, 1, ORAL_INFUSION),
+]:
+    timelines.append(dict(kernel=kernel, params=params, ops=fixture["ops"], predictions=simulate(kernel, kp, v, out_state, fixture["ops"])))
+json.dump(timelines, open(os.path.join(OUT, "timelines.json"), "w"), indent=0)
+
+# ---- stiff_c4.json: Radau rtol=1e-12 ---------------------------------------------------------------------
+stiff = []
+for trial in range(6):
+    vmax, km, v, ke0, emax, ec50 = [float(z) for z in (10 + 50 * rng.random(), 0.2 + 4.8 * rng.random(), 15 + 45 * rng.random(),
+                                                        [0.5, 5.0, 20.0, 50.0, 50.0, 35.0][trial], 50 + 100 * rng.random(), 1 + 9 * rng.random())]
+    load, inf = 200.0, 150.0
+    t_obs = [0.5, 1, 2, 4, 8, 12, 18, 24]
+    segs = [(0.0, 6.0, 0.0), (6.0, 7.0, inf), (7.0, 12.0, 0.0), (12.0, 13.0, inf), (13.0, 18.0, 0.0), (18.0, 19.0, inf), (19.0, 24.0, 0.0)]
+    x = np.array([load, 0.0])
+    cp, eff = {}, {}
+    for a, b, r in segs:
+        def rhs(t, y, r=r):
+            c = y[0] / v
+            return [-vmax * c / (km + c) + r, ke0 * (c - y[1])]
+        ts = [t for t in t_obs if a < t <= b]
+        sol = solve_ivp(rhs, (a, b), x, method="Radau", rtol=1e-12, atol=1e-14, t_eval=ts + ([b] if (not ts or ts[-1] != b) else []))
+        for k, t in enumerate(ts):
+            cp[t] = sol.y[0, k] / v
+            eff[t] = emax * sol.y[1, k] / (ec50 + sol.y[1, k])
+        x = sol.y[:, -1]
+    ops = [("bolus", 0.0, load, "load")] + [("infusion", t0, inf, "iv", 1.0) for t0 in (6.0, 12.0, 18.0)]
+    preds = []
+    for k, t in enumerate(t_obs):
+        ops.append(("missing_observation", float(t), "cp" if k % 2 == 0 else "effect"))
+        preds.append(cp[t] if k % 2 == 0 else eff[t])
+    stiff.append(dict(params=[vmax, km, v, ke0, emax, ec50], ops=ops, predictions=preds))
+json.dump(stiff, open(os.path.join(OUT, "stiff_c4.json"), "w"), indent=0)
+
+# ---- normal.json -----------------------------------------------------------------------------------------------
+mp.mp.dps = 50
+norm = []
+for obs, pred, sigma in [(0, 0, 1), (1.0, 1.0, 0.3), (2.5, 1.0, 0.5), (0.1, 4.0, 0.2), (10.0, 2.0, 0.2), (-3.0, 0.5, 1.5), (1.0, 40.0, 1.0), (40.0, 1.0, 1.0)]:
+    z = (mp.mpf(obs) - mp.mpf(pred)) / mp.mpf(sigma)
+    logpdf = -mp.log(2 * mp.pi) / 2 - mp.log(sigma) - z * z / 2
+    cdf = mp.ncdf(z)
+    sf = mp.ncdf(-z)
+    norm.append(dict(obs=obs, pred=pred, sigma=sigma, logpdf=float(logpdf), logcdf=float(mp.log(cdf)), logsf=float(mp.log(sf))))
+json.dump(norm, open(os.path.join(OUT, "normal.json"), "w"), indent=0)
+print("wrote", sorted(os.listdir(OUT)))
