@@ -178,7 +178,8 @@ int32_t pharmsol_cuda_log_likelihood_matrix(pcu_ctx* ctx, pcu_model* m, pcu_popu
 /* Same with everything resident in HBM (no copies in the call):
  *   spp_soa_dev   device, parameter-major SoA: spp[k*ld_spp + j]
  *   out_dev       device, column-major: out[i + j*ld_out], ld_out >= nsub
- *   stream        cudaStream_t to launch on (NULL = the context's stream); the call is asynchronous,
+ *   stream        cudaStream_t to launch on (NULL = the context's own non-blocking stream; pass
+ *                 cudaStreamLegacy / cudaStreamPerThread for the default streams); the call is asynchronous,
  *                 errors of the launch are collected by pharmsol_cuda_collect_errors after a sync. */
 int32_t pharmsol_cuda_log_likelihood_matrix_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
                                                    const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,

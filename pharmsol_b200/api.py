@@ -542,19 +542,23 @@ class ResidentPsi:
         self.ld_spp = max(self.ncols, 1)
         self.spp_soa = torch.empty((self.nparams, self.ld_spp), dtype=torch.float64, device=self.device)
         if self.ncols:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.upload_support_points(self.ctx, spp[lo:hi], self.spp_soa.data_ptr(), self.ld_spp, stream)
+            _lib.upload_support_points(self.ctx, spp[lo:hi], self.spp_soa.data_ptr(), self.ld_spp, self._stream())
             torch.cuda.current_stream(self.device).synchronize()
         equation._model.compile(self.ctx)
+
+    def _stream(self):
+        """torch's current stream as a cudaStream_t; the legacy default stream (handle 0) is passed as
+        cudaStreamLegacy (0x1) because NULL means "the context's own stream" in the C ABI."""
+        h = self.torch.cuda.current_stream(self.device).cuda_stream
+        return h if h else 1
 
     def launch(self):
         """One asynchronous psi kernel launch for this rank's columns (no copies, no sync)."""
         if not self.ncols:
             return
         slab = self.sharded.local_slab()
-        stream = self.torch.cuda.current_stream(self.device).cuda_stream
         _lib.log_likelihood_matrix_device(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,
-                                          slab.data_ptr(), self.nsub, self.first_col, stream)
+                                          slab.data_ptr(), self.nsub, self.first_col, self._stream())
 
     def step(self):
         """launch + all-gather of the column slabs (no-op on one rank); asynchronous."""
