@@ -121,6 +121,8 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
             st.t = __ldg(pop.occ_t0 + occ);
             st.h = -1.0;
             st.have_k1 = false;
+            st.h_post = -1.0;
+            st.since_restart = 0;
             bnd = __ldg(pop.bnd_offsets + occ);
             bnd_end = __ldg(pop.bnd_offsets + occ + 1);
         }
@@ -260,8 +262,14 @@ __device__ __forceinline__ void psi_dispatch(const PopView& pop, const double* _
 }  // namespace psi
 
 // The emitted translation unit instantiates:  PSI_DEFINE_ENTRY(Model, SOLVER, psi_entry_<id>)
+#ifndef PSI_MAX_THREADS
+#define PSI_MAX_THREADS 128
+#endif
+#ifndef PSI_MIN_BLOCKS
+#define PSI_MIN_BLOCKS 1
+#endif
 #define PSI_DEFINE_ENTRY(MODEL, SOLVER, NAME)                                                                 \
-    extern "C" __global__ void __launch_bounds__(128)                                                         \
+    extern "C" __global__ void __launch_bounds__(PSI_MAX_THREADS, PSI_MIN_BLOCKS)                             \
     NAME(psi::PopView pop, const double* __restrict__ spp, long long ncols, long long spp_ld, psi::RunOpts opt, \
          psi::OutView out) {                                                                                  \
         psi::psi_dispatch<MODEL, SOLVER>(pop, spp, ncols, spp_ld, opt, out);                                  \

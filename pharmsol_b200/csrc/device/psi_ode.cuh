@@ -15,6 +15,39 @@
 
 namespace psi {
 
+// reciprocal to ~2^-20 with ONE MUFU.RCP64H and no Newton refinement: enough for the weights of an
+// error norm, and it moves the work from the FP64 pipe (the bound of these kernels) to the XU pipe.
+PSI_DEV double rcp_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+// The tableau coefficients live in the constant bank so DFMA reads them as c[3][..] operands; as
+// constexpr literals the compiler re-materialises each 64-bit immediate with two UMOVs per use
+// (88 UMOV per Dopri5 step in the first build).  The constexpr copies stay for compile-time zero tests.
+#define PSI_DP5_A \
+    {0, 0, 0, 0, 0, 0}, {1.0 / 5, 0, 0, 0, 0, 0}, {3.0 / 40, 9.0 / 40, 0, 0, 0, 0}, {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0}, \
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0}, \
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0}, \
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}
+#define PSI_DP5_E \
+    35.0 / 384 - 5179.0 / 57600, 0.0, 500.0 / 1113 - 7571.0 / 16695, 125.0 / 192 - 393.0 / 640, -2187.0 / 6784 + 92097.0 / 339200, \
+    11.0 / 84 - 187.0 / 2100, -1.0 / 40
+#define PSI_TS5_A \
+    {0, 0, 0, 0, 0, 0}, {0.161, 0, 0, 0, 0, 0}, {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0}, \
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0}, \
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0}, \
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0}, \
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}
+#define PSI_TS5_E \
+    -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, 0.5823571654525552, \
+    -0.45808210592918697, 0.015151515151515152
+static __constant__ double kDp5A[7][6] = {PSI_DP5_A};
+static __constant__ double kDp5E[7] = {PSI_DP5_E};
+static __constant__ double kTs5A[7][6] = {PSI_TS5_A};
+static __constant__ double kTs5E[7] = {PSI_TS5_E};
+
 struct Dopri5 {
     static constexpr int S = 7;
     __host__ __device__ static constexpr double c(int s) {
@@ -22,20 +55,14 @@ struct Dopri5 {
         return C[s];
     }
     __host__ __device__ static constexpr double a(int s, int j) {
-        constexpr double A[7][6] = {
-            {0, 0, 0, 0, 0, 0},
-            {1.0 / 5, 0, 0, 0, 0, 0},
-            {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
-            {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
-            {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
-            {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-            {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+        constexpr double A[7][6] = {PSI_DP5_A};
         return A[s][j];
     }
+    PSI_DEV static double ca(int s, int j) { return kDp5A[s][j]; }
+    PSI_DEV static double ce(int j) { return kDp5E[j]; }
     // b - bhat
     __host__ __device__ static constexpr double e(int j) {
-        constexpr double E[7] = {35.0 / 384 - 5179.0 / 57600, 0.0, 500.0 / 1113 - 7571.0 / 16695, 125.0 / 192 - 393.0 / 640,
-                                 -2187.0 / 6784 + 92097.0 / 339200, 11.0 / 84 - 187.0 / 2100, -1.0 / 40};
+        constexpr double E[7] = {PSI_DP5_E};
         return E[j];
     }
 };
@@ -47,19 +74,13 @@ struct Tsit5 {
         return C[s];
     }
     __host__ __device__ static constexpr double a(int s, int j) {
-        constexpr double A[7][6] = {
-            {0, 0, 0, 0, 0, 0},
-            {0.161, 0, 0, 0, 0, 0},
-            {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
-            {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
-            {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
-            {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
-            {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+        constexpr double A[7][6] = {PSI_TS5_A};
         return A[s][j];
     }
+    PSI_DEV static double ca(int s, int j) { return kTs5A[s][j]; }
+    PSI_DEV static double ce(int j) { return kTs5E[j]; }
     __host__ __device__ static constexpr double e(int j) {
-        constexpr double E[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
-                                 0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+        constexpr double E[7] = {PSI_TS5_E};
         return E[j];
     }
 };
@@ -71,15 +92,23 @@ struct OdeState {
     double h;          // next trial step; <= 0 means "pick automatically" (restart)
     double k1[N];      // f(t, y) when have_k1 (FSAL)
     bool have_k1;
+    // Restart memory: the step size the controller had settled on shortly after the previous restart
+    // (periodic dosing => the same transient recurs), tried first at the next restart instead of
+    // ramping up again from the Hairer starting step.  <= 0: none yet.
+    double h_post;
+    int since_restart;
 };
+#ifndef PSI_RESTART_REUSE
+#define PSI_RESTART_REUSE 1
+#endif
 
 template <int N>
 PSI_DEV double rms_scaled(const double* v, const double* y, double rtol, double atol) {
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const double q = v[i] / (atol + rtol * fabs(y[i]));
-        s += q * q;
+        const double q = v[i] * rcp_approx(fma(rtol, fabs(y[i]), atol));
+        s = fma(q, q, s);
     }
     return sqrt(s * (1.0 / N));
 }
@@ -118,7 +147,11 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
             cnt.evals++;
             st.have_k1 = true;
         }
-        if (!(st.h > 0.0)) st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
+        if (!(st.h > 0.0)) {
+            st.since_restart = 0;
+            if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
+            else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
+        }
         const double rem = tstop - st.t;
         const bool last = st.h >= rem;
         const double h = last ? rem : st.h;
@@ -132,35 +165,39 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < s; ++j)
-                    if (TAB::a(s, j) != 0.0) acc = fma(TAB::a(s, j), k[j][i], acc);
+                    if (TAB::a(s, j) != 0.0) acc = fma(TAB::ca(s, j), k[j][i], acc);
                 ynew[i] = fma(h, acc, st.y[i]);
             }
             f(st.t + TAB::c(s) * h, ynew, k[s]);
         }
         cnt.evals += TAB::S - 1;
-        // ynew = 5th-order solution (FSAL: stage S-1 is f(t+h, ynew))
+        // ynew = 5th-order solution (FSAL: stage S-1 is f(t+h, ynew)).
+        // Error norm: the embedded difference sum stays in FP64 (it is a cancellation of O(1) terms down
+        // to ~tol); the per-component weight 1/sc uses the one-MUFU reciprocal and the controller runs
+        // in FP32 on the SFU: none of this steers anything but h.
         double err2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double e = 0.0;
 #pragma unroll
             for (int j = 0; j < TAB::S; ++j)
-                if (TAB::e(j) != 0.0) e = fma(TAB::e(j), k[j][i], e);
-            const double sc = atol + rtol * fmax(fabs(st.y[i]), fabs(ynew[i]));
-            const double q = (h * e) / sc;
+                if (TAB::e(j) != 0.0) e = fma(TAB::ce(j), k[j][i], e);
+            const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
+            const double q = (h * e) * rcp_approx(sc);
             err2 = fma(q, q, err2);
         }
-        const double err = sqrt(err2 * (1.0 / N));
-        if (!(err == err) || err > 1e300) {
+        if (!(err2 <= 1e300)) {
             // non-finite error estimate: treat as a rejected step with the maximum shrink
             cnt.rejected++;
             st.h = h * 0.2;
             if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
             continue;
         }
-        float fac = (err <= 1e-30) ? 10.0f : 0.9f * __powf((float)err, -0.2f);
+        // fac = 0.9 * err^(-1/5), err = sqrt(err2 / N)  =>  0.9 * (err2 / N)^(-1/10)
+        const float e2 = (float)err2 * (1.0f / N);
+        float fac = (e2 <= 1e-30f) ? 10.0f : 0.9f * __powf(e2, -0.1f);
         fac = fminf(10.0f, fmaxf(0.2f, fac));
-        if (err <= 1.0) {
+        if (err2 <= (double)N) {
             cnt.steps++;
             st.t = last ? tstop : st.t + h;
 #pragma unroll
@@ -168,6 +205,7 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
             // a step clipped by tstop must not shrink the controller's step estimate
             const double hn = h * (double)fac;
             st.h = (last && hn < st.h) ? st.h : hn;
+            if (PSI_RESTART_REUSE && ++st.since_restart == 2) st.h_post = st.h;
         } else {
             cnt.rejected++;
             st.h = h * (double)fminf(1.0f, fac);
