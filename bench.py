@@ -44,7 +44,7 @@ WORKLOADS = {
     "c1": dict(nsub=1000, nspp=1000, solver=None),
     "c2": dict(nsub=500, nspp=20000, solver="Dopri5"),
     "c3": dict(nsub=10000, nspp=6250, solver=None),        # 50k columns / 8 GPUs = 6,250 per GPU
-    "c4": dict(nsub=2000, nspp=10000, solver="Sdirk4"),
+    "c4": dict(nsub=2000, nspp=10000, solver="Rodas4"),
     "c5": dict(nsub=200, nspp=5000, solver=None),
 }
 # SURVEY §8d op weights: add/sub/mul = 1, fma = 2, div = sqrt = 10, exp = log = 24, sincos = 40 each, atan2 = 50, pow = 60
@@ -156,7 +156,8 @@ def config_dict(args, w, nsub, nspp_per_gpu, world):
     if w["kind"] == "ode":
         cfg.update(solver=WORKLOADS[args.workload]["solver"], rtol=args.tol, atol=args.tol)
     if w["kind"] == "sde":
-        cfg.update(particles=args.particles, sde_mode="mean-prediction (what log_likelihood_matrix evaluates, SURVEY F3)")
+        cfg.update(particles=args.particles, sde_mode="particle filter (SDE::estimate_log_likelihood, sde/mod.rs:526-577)",
+                   stepper="reference adaptive Euler-Maruyama (sde/em.rs:134-167)")
     return cfg
 
 
@@ -181,14 +182,17 @@ def cpu_reference_rate(args, w, nsub, budget_s, threads=0):
         kw = dict(particles=args.particles)
     om, od, oe = H.oracle_objects(w, **kw)
     spp = w["support_points"]
-    s = min(len(spp), 64)
+    s = min(len(spp), 64 if w["kind"] != "sde" else 1)
     t0 = time.perf_counter()
-    om.log_likelihood_matrix(od, spp[:s], oe, nthreads=threads)
+    mkw = dict(sde_mode=1) if w["kind"] == "sde" else {}
+    om.log_likelihood_matrix(od, spp[:s], oe, nthreads=threads, **mkw)
     probe = time.perf_counter() - t0
     rate = nsub * s / max(probe, 1e-9)
     s2 = int(min(len(spp), max(s, rate * budget_s / nsub)))
+    if w["kind"] == "sde":
+        s2 = min(s2, 2)      # attempt counts vary strongly with (ke, sigma): keep the sample bounded
     t0 = time.perf_counter()
-    _, info = om.log_likelihood_matrix(od, spp[:s2], oe, nthreads=threads, return_info=True)
+    _, info = om.log_likelihood_matrix(od, spp[:s2], oe, nthreads=threads, return_info=True, **mkw)
     dt = time.perf_counter() - t0
     return nsub * s2 / dt, {"cores": int(info["threads"]), "sample": f"{nsub} subjects x first {s2} support points of the workload, {dt:.1f} s",
                             "seconds": dt, "nspp_sample": s2}
@@ -269,7 +273,7 @@ def run_product(args):
     if w["kind"] == "ode":
         eq.with_solver(getattr(ps.OdeSolver, cfg["solver"])).with_tolerances(args.tol, args.tol)
     if w["kind"] == "sde":
-        eq.with_particles(args.particles)
+        eq.with_particles(args.particles).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.ReferenceAdaptive)
     job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev)
     ctx = job.ctx
     npairs_rank = nsub * job.ncols
@@ -304,7 +308,8 @@ def run_product(args):
     kernel_ms_avg = float(np.mean(kern_ms))
     counters = ctx.last_counters                             # of the last launch (every launch does identical work)
     value = npairs_total * args.steps / (total_ms * 1e-3)
-    finite = bool(torch.isfinite(psi).all().item())
+    n_nan = int(torch.isnan(psi).sum().item())               # NaN marks a failed pair (none expected)
+    n_neginf = int(torch.isneginf(psi).sum().item())         # -inf is a legitimate particle-filter result (sde/mod.rs:699-703)
 
     nobs, nsteps = events_per_subject(w)
     flops = algorithmic_flops(args.workload, npairs_rank, counters, nobs, nsteps)
@@ -362,7 +367,7 @@ def run_product(args):
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_dict(args, w, nsub, nspp_per_gpu, world),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "all_finite": finite, "wall_s_timed_region": t_wall, "fp64_peak_clock_mhz": clk}
+                "psi_nan": n_nan, "psi_neg_inf": n_neginf, "wall_s_timed_region": t_wall, "fp64_peak_clock_mhz": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -58,8 +58,9 @@ enum { PCU_KIND_ODE = 0, PCU_KIND_ANALYTICAL = 1, PCU_KIND_SDE = 2 };        /* 
 enum { PCU_CENSOR_NONE = 0, PCU_CENSOR_BLOQ = 1, PCU_CENSOR_ALOQ = 2 };      /* Censor, data/event.rs:559-567    */
 enum { PCU_ERRMODEL_NONE = 0, PCU_ERRMODEL_ADDITIVE = 1, PCU_ERRMODEL_PROPORTIONAL = 2 }; /* error_model.rs:786 */
 /* OdeSolver (ode/mod.rs:59-84).  The reference offers Bdf | Sdirk(TrBdf2|Esdirk34) | ExplicitRk(Tsit45)
- * through diffsol; this backend offers two explicit and two implicit register-resident solvers. */
-enum { PCU_SOLVER_DOPRI5 = 0, PCU_SOLVER_TSIT45 = 1, PCU_SOLVER_SDIRK4 = 2, PCU_SOLVER_TRBDF2 = 3 };
+ * through diffsol; this backend offers two explicit pairs, two SDIRK methods and a Rosenbrock method (RODAS4), all
+ * register-resident per thread. */
+enum { PCU_SOLVER_DOPRI5 = 0, PCU_SOLVER_TSIT45 = 1, PCU_SOLVER_SDIRK4 = 2, PCU_SOLVER_TRBDF2 = 3, PCU_SOLVER_RODAS4 = 4 };
 /* Analytical `derive` time semantics: sub-interval END (DSL runtime,
  * dsl/native.rs:1903-1916) or sub-interval LENGTH (analytical! macro, analytical/mod.rs:362-364). */
 enum { PCU_COVTIME_INTERVAL_END = 0, PCU_COVTIME_INTERVAL_LENGTH = 1 };

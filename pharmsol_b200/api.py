@@ -196,12 +196,13 @@ class AssayErrorModels:
 class OdeSolver:
     """ode/mod.rs:59-84.  The reference's solvers come from diffsol; this backend provides two
     explicit pairs and two implicit (stiff) methods.  `Bdf` (the reference default for stiff
-    problems) and `Esdirk34` select the order-4 SDIRK."""
+    problems) selects the Rosenbrock method RODAS4, `Esdirk34` the order-4 SDIRK."""
     Dopri5 = 0
     Tsit45 = 1
     Sdirk4 = 2
     TrBdf2 = 3
-    Bdf = 2
+    Rodas4 = 4      # Rosenbrock (linearly implicit, no Newton iteration): the stiff workhorse on the GPU
+    Bdf = 4
     Esdirk34 = 2
 
 

@@ -48,6 +48,7 @@ PSI_DEV int ode_advance(OdeState<M::NSTATE>& st, double tstop, OdeRhs<M>& f, con
     if constexpr (SOLVER == SOLVER_TSIT5) return erk_integrate_to<Tsit5, M::NSTATE>(st, tstop, f, opt, cnt);
     else if constexpr (SOLVER == SOLVER_SDIRK4) return sdirk4_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
     else if constexpr (SOLVER == SOLVER_TRBDF2) return trbdf2_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
+    else if constexpr (SOLVER == SOLVER_RODAS4) return rodas4_integrate_to<M::NSTATE, M::RHS_TIME_DEP>(st, tstop, f, opt, cnt);
     else return erk_integrate_to<Dopri5, M::NSTATE>(st, tstop, f, opt, cnt);
 }
 
@@ -265,8 +266,12 @@ __device__ __forceinline__ void psi_dispatch(const PopView& pop, const double* _
 #ifndef PSI_MAX_THREADS
 #define PSI_MAX_THREADS 128
 #endif
+// 6 resident CTAs of 128 threads per SM (<= 80 registers per thread): measured on B200, the closed-form
+// 3-compartment kernel gains 1.66x and the stiff kernels 1.4x over the unconstrained build (which the
+// compiler fills with hoisted loop invariants at 140-180 registers, 3 warps per scheduler), while the
+// 96-register Dopri5 kernel of the 3-state model loses 2 %.  (scripts/tune.py, profiles/r01_tuning.md)
 #ifndef PSI_MIN_BLOCKS
-#define PSI_MIN_BLOCKS 1
+#define PSI_MIN_BLOCKS 6
 #endif
 #define PSI_DEFINE_ENTRY(MODEL, SOLVER, NAME)                                                                 \
     extern "C" __global__ void __launch_bounds__(PSI_MAX_THREADS, PSI_MIN_BLOCKS)                             \

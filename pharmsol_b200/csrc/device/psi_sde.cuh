@@ -19,7 +19,7 @@
 // index out of bounds).
 // The reference RNG is an unseeded thread-local ChaCha (rand 0.10), so parity is statistical only.
 #pragma once
-#include "psi_common.cuh"
+#include "psi_ode.cuh"
 
 namespace psi {
 
@@ -40,33 +40,35 @@ struct Philox {
     }
 };
 
-// Per-particle normal stream: Box-Muller on 32-bit uniforms in FP32 (SFU), 4 normals per block.
+// Per-particle normal stream: Box-Muller on 24-bit uniforms in FP32 (SFU); one Philox block = 4 normals.
+// Everything is indexed statically so the normals stay in registers (a runtime-indexed buffer would
+// live in local memory).
 struct NormalStream {
     Philox ph;
     unsigned int c0, c2, c3;   // particle slot, interval sequence, pair
     unsigned int ctr;          // draw-block counter within the interval
-    float buf[4];
-    int have;
     PSI_DEV void reset(unsigned int particle, unsigned int seq, unsigned int pair) {
-        c0 = particle; c2 = seq; c3 = pair; ctr = 0; have = 0;
+        c0 = particle; c2 = seq; c3 = pair; ctr = 0;
     }
-    PSI_DEV double next() {
-        if (have == 0) {
-            unsigned int r[4];
-            ph(c0, ctr++, c2, c3, r);
+    PSI_DEV void block4(float* z) {
+        unsigned int r[4];
+        ph(c0, ctr++, c2, c3, r);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float u1 = ((float)(r[2 * i] >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
-                const float u2 = ((float)(r[2 * i + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                const float rad = sqrtf(-2.0f * __logf(u1));
-                float s, c;
-                __sincosf(6.2831853071795865f * u2, &s, &c);
-                buf[2 * i] = rad * c;
-                buf[2 * i + 1] = rad * s;
-            }
-            have = 4;
+        for (int i = 0; i < 2; ++i) {
+            const float u1 = ((float)(r[2 * i] >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
+            const float u2 = ((float)(r[2 * i + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.2831853071795865f * u2, &sn, &cs);
+            z[2 * i] = rad * cs;
+            z[2 * i + 1] = rad * sn;
         }
-        return (double)buf[--have];
+    }
+    // COUNT normals into z[0..COUNT) (z must hold 4*ceil(COUNT/4) floats)
+    template <int COUNT>
+    PSI_DEV void fill(float* z) {
+#pragma unroll
+        for (int b = 0; b < (COUNT + 3) / 4; ++b) block4(z + 4 * b);
     }
 };
 PSI_DEV double philox_uniform(const Philox& ph, unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3) {
@@ -91,27 +93,60 @@ PSI_DEV double block_sum(double v, double* smem4) {
     return s;
 }
 
+// sqrt(x) for x > 0 to ~1e-12 relative: MUFU.RSQ64H seed + one Newton step (the noise amplitude
+// sqrt(dt) does not need the last bits; a full FP64 sqrt is ~25 instructions on the bound pipe)
+PSI_DEV double sqrt_fast(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);       // r <- r (1.5 - 0.5 x r^2)
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    return x * r;
+}
+
 template <class M>
 struct SdeStep {
+    static constexpr int NS = M::NSTATE;
+    static constexpr int NR = AtLeast1<M::NROUTE>::v;
     PairCtx<M>& c;
     InfRange inf;
+    // the active infusion rates are piecewise constant: c.rate is valid for rate_from <= t < rate_until
+    double rate_from, rate_until;
+    PSI_DEV SdeStep(PairCtx<M>& cc, InfRange r) : c(cc), inf(r), rate_from(1.0), rate_until(0.0) {}
+    PSI_DEV void invalidate_rates() { rate_from = 1.0; rate_until = 0.0; }
+    // drift rule of the reference: every infusion with start <= t <= start + duration (sde/mod.rs:124-133)
+    PSI_DEV void rates_at(double t) {
+        if (t >= rate_from && t < rate_until) return;
+        double until = psi_inf();
+#pragma unroll
+        for (int k = 0; k < NR; ++k) c.rate[k] = 0.0;
+        for (int i = 0; i < inf.n; ++i) {
+            double s, d, a; int input;
+            load_inf(inf.p + i, s, d, a, input);
+            const double e = s + d;
+            if (t >= s && t <= e) add_rate<NR>(c.rate, input, a / d);
+            if (s > t) until = fmin(until, s);
+            if (e >= t) until = fmin(until, e);
+        }
+        rate_from = t;
+        rate_until = until;       // at t == until the set is recomputed (closed interval ends)
+    }
     // drift + diffusion at (t, x): derive/covariates refreshed at absolute t (native.rs:2330-2420)
     PSI_DEV void eval(double t, const double* x, double* dx, double* g) {
-        constexpr int NR = AtLeast1<M::NROUTE>::v;
-        active_rates<NR>(inf, t, c.rate);
+        rates_at(t);
         if constexpr (M::RHS_USES_COV) fill_cov<M>(*c.pop, c.occ, t, c.cov);
         if constexpr (M::HAS_DERIVE && M::DERIVE_DEPS != 0) M::derive(t, x, c.p, c.cov, c.rate, c.d);
         M::drift(t, x, c.p, c.cov, c.rate, c.d, dx);
 #pragma unroll
-        for (int k = 0; k < M::NSTATE; ++k) g[k] = 0.0;
+        for (int k = 0; k < NS; ++k) g[k] = 0.0;
         M::diffusion(t, x, c.p, c.cov, c.rate, c.d, g);
     }
     // em.rs:104-120
-    PSI_DEV void em_step(double t, double dt, double sqdt, double* x, NormalStream& rng) {
-        double dx[M::NSTATE], g[M::NSTATE];
+    PSI_DEV void em_step(double t, double dt, double sqdt, double* x, const float* z) {
+        double dx[NS], g[NS];
         eval(t, x, dx, g);
 #pragma unroll
-        for (int k = 0; k < M::NSTATE; ++k) x[k] += dx[k] * dt + g[k] * rng.next() * sqdt;
+        for (int k = 0; k < NS; ++k) x[k] = fma(dx[k], dt, fma(g[k] * (double)z[k], sqdt, x[k]));
     }
     // em.rs:134-167
     PSI_DEV void solve_reference(double t0, double tf, double* x, NormalStream& rng, Counters& cnt) {
@@ -119,27 +154,30 @@ struct SdeStep {
         int guard = 0;
         while (t < tf) {
             if (++guard > 4000000) break;
-            double y1[M::NSTATE], y2[M::NSTATE];
+            double y1[NS], y2[NS];
 #pragma unroll
-            for (int k = 0; k < M::NSTATE; ++k) { y1[k] = x[k]; y2[k] = x[k]; }
-            const double sq = sqrt(dt), sqh = sqrt(dt / 2.0);
-            em_step(t, dt, sq, y1, rng);
-            em_step(t, dt / 2.0, sqh, y2, rng);
-            em_step(t + dt / 2.0, dt / 2.0, sqh, y2, rng);
+            for (int k = 0; k < NS; ++k) { y1[k] = x[k]; y2[k] = x[k]; }
+            float z[4 * ((3 * NS + 3) / 4)];
+            rng.template fill<3 * NS>(z);                     // three INDEPENDENT draws per state (em.rs:104-120)
+            const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
+            em_step(t, dt, sq, y1, z);
+            em_step(t, dt * 0.5, sqh, y2, z + NS);
+            em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
             cnt.evals += 3;
+            // err only steers dt: the weight 1/tol uses the one-MUFU reciprocal and the new step the FP32 rsqrt
             double err = 0.0;
 #pragma unroll
-            for (int k = 0; k < M::NSTATE; ++k) {
-                const double tol = 1e-2 + 1e-2 * fabs(x[k]);
-                err = fmax(err, fabs(y1[k] - y2[k]) / tol);
+            for (int k = 0; k < NS; ++k) {
+                const double tol = fma(1e-2, fabs(x[k]), 1e-2);
+                err = fmax(err, fabs(y1[k] - y2[k]) * rcp_approx(tol));
             }
-            double nd = dt * 0.9 * sqrt(1.0 / err);
+            double nd = dt * (double)(0.9f * rsqrtf((float)err));
             nd = fmin(fmax(nd, 1e-6), 0.1);
             if (err <= 1.0) {
                 cnt.steps++;
                 t += dt;
 #pragma unroll
-                for (int k = 0; k < M::NSTATE; ++k) x[k] = y2[k];
+                for (int k = 0; k < NS; ++k) x[k] = y2[k];
                 dt = fmin(nd, tf - t);
             } else {
                 cnt.rejected++;
@@ -147,10 +185,73 @@ struct SdeStep {
             }
         }
     }
+    // The reference stepper over ALL particles of the CTA with lane-level dynamic scheduling: the number of
+    // attempts per particle is random (the error estimate is noise-dominated), so a static particle->lane
+    // map leaves a quarter of the lanes idle (ncu: 24.0 active threads per instruction).  Here every lane
+    // runs one flat "one attempt" loop and fetches the next particle from a CTA-wide counter the moment its
+    // own finishes.  Results do not depend on the schedule: the Philox stream is keyed by the particle.
+    PSI_DEV void solve_reference_all(double t0, double tf, double* buf, int np, int* next, NormalStream& rng,
+                                     unsigned int seq, unsigned int pair, Counters& cnt) {
+        double x[NS];
+        double t = t0, dt = 0.1;
+        int k = -1, guard = 0;
+        bool active = false;
+        while (true) {
+            if (!active) {
+                k = atomicAdd(next, 1);
+                if (k >= np) break;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) x[s] = buf[(long long)s * np + k];
+                rng.reset((unsigned int)k, seq, pair);
+                t = t0; dt = 0.1; guard = 0; active = true;
+            }
+            double y1[NS], y2[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) { y1[q] = x[q]; y2[q] = x[q]; }
+            float z[4 * ((3 * NS + 3) / 4)];
+            rng.template fill<3 * NS>(z);
+            const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
+            em_step(t, dt, sq, y1, z);
+            em_step(t, dt * 0.5, sqh, y2, z + NS);
+            em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
+            cnt.evals += 3;
+            double err = 0.0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                const double tol = fma(1e-2, fabs(x[q]), 1e-2);
+                err = fmax(err, fabs(y1[q] - y2[q]) * rcp_approx(tol));
+            }
+            double nd = dt * (double)(0.9f * rsqrtf((float)err));
+            nd = fmin(fmax(nd, 1e-6), 0.1);
+            if (err <= 1.0) {
+                cnt.steps++;
+                t += dt;
+#pragma unroll
+                for (int q = 0; q < NS; ++q) x[q] = y2[q];
+                dt = fmin(nd, tf - t);
+            } else {
+                cnt.rejected++;
+                dt = nd;
+            }
+            if (!(t < tf) || ++guard > 4000000) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) buf[(long long)s * np + k] = x[s];
+                active = false;
+            }
+        }
+    }
     PSI_DEV void solve_fixed(double t0, double tf, double hmax, double* x, NormalStream& rng, Counters& cnt) {
         const int n = (int)fmax(1.0, ceil((tf - t0) / hmax - 1e-9));
         const double dt = (tf - t0) / n, sq = sqrt(dt);
-        for (int i = 0; i < n; ++i) em_step(t0 + i * dt, dt, sq, x, rng);
+        // one Philox block yields 4 normals: take G = 4 / NS steps per block when NS < 4
+        constexpr int G = (NS >= 4) ? 1 : 4 / NS;
+        for (int i = 0; i < n; i += G) {
+            float z[4 * ((G * NS + 3) / 4)];
+            rng.template fill<G * NS>(z);
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (i + q < n) em_step(fma((double)(i + q), dt, t0), dt, sq, x, z + q * NS);
+        }
         cnt.steps += n; cnt.evals += n;
     }
 };
@@ -163,6 +264,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
         constexpr int NS = M::NSTATE;
         constexpr int NR = AtLeast1<M::NROUTE>::v;
         __shared__ double red[8];
+        __shared__ int next_particle;
         const int np = opt.nparticles;
         const int tid = threadIdx.x, B = blockDim.x;
         double* ws = out.scratch + (long long)blockIdx.x * out.scratch_stride;
@@ -200,7 +302,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
             for (int occ = occ0; occ < occ1; ++occ) {
                 c.occ = occ;
                 const InfRange inf = occ_infusions(pop, occ);
-                SdeStep<M> stepper{c, inf};
+                SdeStep<M> stepper(c, inf);
                 double x0[NS];
 #pragma unroll
                 for (int k = 0; k < NS; ++k) x0[k] = 0.0;
@@ -257,6 +359,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
 #pragma unroll
                             for (int s = 0; s < NS; ++s) x[s] = cur_buf[(long long)s * np + k];
                             active_rates<NR>(inf, te, c.rate);
+                            stepper.invalidate_rates();
                             c.refresh(te, x);
                             double y[AtLeast1<M::NOUT>::v];
 #pragma unroll
@@ -329,15 +432,21 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                     if (have && te != tn) {
                         ++seq;
                         __syncthreads();
-                        for (int k = tid; k < np; k += B) {
-                            double x[NS];
+                        stepper.invalidate_rates();     // lag / fa / outputs above reuse c.rate as scratch
+                        if (opt.em_mode == EM_FIXED_STEP) {
+                            for (int k = tid; k < np; k += B) {
+                                double x[NS];
 #pragma unroll
-                            for (int s = 0; s < NS; ++s) x[s] = cur_buf[(long long)s * np + k];
-                            rng.reset((unsigned int)k, seq, (unsigned int)pair);
-                            if (opt.em_mode == EM_FIXED_STEP) stepper.solve_fixed(te, tn, opt.em_dt, x, rng, cnt);
-                            else stepper.solve_reference(te, tn, x, rng, cnt);
+                                for (int s = 0; s < NS; ++s) x[s] = cur_buf[(long long)s * np + k];
+                                rng.reset((unsigned int)k, seq, (unsigned int)pair);
+                                stepper.solve_fixed(te, tn, opt.em_dt, x, rng, cnt);
 #pragma unroll
-                            for (int s = 0; s < NS; ++s) cur_buf[(long long)s * np + k] = x[s];
+                                for (int s = 0; s < NS; ++s) cur_buf[(long long)s * np + k] = x[s];
+                            }
+                        } else {
+                            if (tid == 0) next_particle = 0;
+                            __syncthreads();
+                            stepper.solve_reference_all(te, tn, cur_buf, np, &next_particle, rng, seq, (unsigned int)pair, cnt);
                         }
                         __syncthreads();
                     }
@@ -350,8 +459,9 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                 if (out.ll) out.ll[(long long)subj + j * out.ld_ll] = ll;
             }
             __syncthreads();
+            flush_counters(out, cnt);      // per pair: the 32-bit per-thread counters would wrap over a long grid-stride loop
+            cnt = Counters{};
         }
-        flush_counters(out, cnt);
     }
 }
 

@@ -273,4 +273,151 @@ PSI_DEV int trbdf2_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
     return dirk_integrate_to<TrBdf2Tab, N>(st, tstop, f, opt, cnt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// RODAS4 (Hairer & Wanner, "Solving ODEs II", IV.7; coefficients of the authors' RODAS code, METH=1):
+// 6-stage stiffly accurate Rosenbrock method of order 4 with an embedded order-3 solution.
+// Linearly implicit: per step ONE Jacobian, ONE LU of (I/(h gamma) - J), six right-hand sides and six
+// triangular solves, and no Newton iteration, so every lane of a warp does the same fixed work per step
+// (the SDIRK methods above diverge on their per-stage Newton counts).  The coefficients were
+// cross-checked by convergence order (4.00 observed) against SciPy Radau before use.
+//   (I/(h g) - J) k_i = f(t + alpha_i h, y + sum_j a_ij k_j) + (1/h) sum_j c_ij k_j + h d_i df/dt
+//   y_new = y + sum a_5j k_j + k_5 + k_6,   error estimate = k_6
+// df/dt is only formed (one extra RHS evaluation) for right-hand sides that depend on time explicitly.
+// ---------------------------------------------------------------------------------------------
+static __constant__ double kRodasA[6][5] = {
+    {0, 0, 0, 0, 0},
+    {0.1544000000000000e+01, 0, 0, 0, 0},
+    {0.9466785280815826e+00, 0.2557011698983284e+00, 0, 0, 0},
+    {0.3314825187068521e+01, 0.2896124015972201e+01, 0.9986419139977817e+00, 0, 0},
+    {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 0},
+    {0, 0, 0, 0, 0}};   // stage 6 continues from stage 5: u += k_5
+static __constant__ double kRodasC[6][5] = {
+    {0, 0, 0, 0, 0},
+    {-0.5668800000000000e+01, 0, 0, 0, 0},
+    {-0.2430093356833875e+01, -0.2063599157091915e+00, 0, 0, 0},
+    {-0.1073529058151375e+00, -0.9594562251023355e+01, -0.2047028614809616e+02, 0, 0},
+    {0.7496443313967647e+01, -0.1024680431464352e+02, -0.3399990352819905e+02, 0.1170890893206160e+02, 0},
+    {0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02, -0.6058818238834054e+01}};
+static __constant__ double kRodasAlpha[6] = {0.0, 0.386, 0.21, 0.63, 1.0, 1.0};
+static __constant__ double kRodasD[6] = {0.25, -0.1043, 0.1035, -0.3620000000000023e-01, 0.0, 0.0};
+
+template <int N, bool TIME_DEP, class F>
+PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
+    const double rtol = opt.rtol, atol = opt.atol;
+    constexpr double g = 0.25;
+    double K[6][N];
+    SmallLU<N> lu;
+    [[maybe_unused]] double T[N];
+    int iters = 0;
+    while (st.t < tstop) {
+        if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
+        if (!st.have_k1) {
+            f(st.t, st.y, st.k1);
+            cnt.evals++;
+            st.have_k1 = true;
+            if constexpr (TIME_DEP) {       // df/dt at (t_n, y_n) by a forward difference
+                const double dlt = 1.4901161193847656e-08 * fmax(1e-5, fabs(st.t)) + 1e-10;
+                f(st.t + dlt, st.y, T);
+                cnt.evals++;
+                const double idl = 1.0 / dlt;
+#pragma unroll
+                for (int i = 0; i < N; ++i) T[i] = (T[i] - st.k1[i]) * idl;
+            }
+        }
+        if (!(st.h > 0.0)) {
+            st.since_restart = 0;
+            if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
+            else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
+        }
+        const double rem = tstop - st.t;
+        const bool last = st.h >= rem;
+        const double h = last ? rem : st.h;
+        const double ih = 1.0 / h;
+        const double ihg = ih * (1.0 / g);
+        // E = I/(h g) - J, factored in registers (J is re-evaluated instead of stored: a Jacobian costs
+        // about one RHS, N*N registers cost occupancy)
+        f.jacobian(st.t, st.y, lu.a);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) lu.a[i * N + j] = ((i == j) ? ihg : 0.0) - lu.a[i * N + j];
+        lu.factor();
+        bool bad = lu.singular;
+        double u[N];
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            double rhs[N];
+            if (s == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) rhs[i] = st.k1[i];
+            } else {
+                if (s < 5) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        double acc = st.y[i];
+#pragma unroll
+                        for (int j = 0; j < s; ++j) acc = fma(kRodasA[s][j], K[j][i], acc);
+                        u[i] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) u[i] += K[4][i];
+                }
+                f(st.t + kRodasAlpha[s] * h, u, rhs);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < s; ++j) acc = fma(kRodasC[s][j], K[j][i], acc);
+                    rhs[i] = fma(ih, acc, rhs[i]);
+                }
+            }
+            if constexpr (TIME_DEP) {
+                if (s < 4) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rhs[i] = fma(h * kRodasD[s], T[i], rhs[i]);
+                }
+            }
+            lu.solve(rhs);
+#pragma unroll
+            for (int i = 0; i < N; ++i) K[s][i] = rhs[i];
+        }
+        cnt.evals += 6;        // 5 right-hand sides + the Jacobian
+        double err2 = 0.0;
+        double ynew[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ynew[i] = u[i] + K[5][i];
+            const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
+            const double q = K[5][i] * rcp_approx(sc);
+            err2 = fma(q, q, err2);
+        }
+        if (bad || !(err2 <= 1e300)) {
+            cnt.rejected++;
+            st.h = h * 0.25;
+            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
+            continue;
+        }
+        // fac = 0.9 * err^(-1/4), err = sqrt(err2 / N)
+        const float e2 = (float)err2 * (1.0f / N);
+        float fac = (e2 <= 1e-30f) ? 6.0f : 0.9f * __powf(e2, -0.125f);
+        fac = fminf(6.0f, fmaxf(0.2f, fac));
+        if (err2 <= (double)N) {
+            cnt.steps++;
+            st.t = last ? tstop : st.t + h;
+#pragma unroll
+            for (int i = 0; i < N; ++i) st.y[i] = ynew[i];
+            st.have_k1 = false;                       // not FSAL: f(t_n, y_n) is evaluated at the new point
+            const double hn = h * (double)fac;
+            st.h = (last && hn < st.h) ? st.h : hn;
+            if (PSI_RESTART_REUSE && ++st.since_restart == 2) st.h_post = st.h;
+        } else {
+            cnt.rejected++;
+            st.h = h * (double)fminf(1.0f, fac);
+            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
+        }
+    }
+    return ST_OK;
+}
+
 }  // namespace psi

@@ -104,7 +104,7 @@ struct PopView {
     int32_t pad;
 };
 
-enum : int { SOLVER_DOPRI5 = 0, SOLVER_TSIT5 = 1, SOLVER_SDIRK4 = 2, SOLVER_TRBDF2 = 3, SOLVER_ROS23 = 4 };
+enum : int { SOLVER_DOPRI5 = 0, SOLVER_TSIT5 = 1, SOLVER_SDIRK4 = 2, SOLVER_TRBDF2 = 3, SOLVER_RODAS4 = 4 };
 enum : int { COVTIME_INTERVAL_END = 0, COVTIME_INTERVAL_LENGTH = 1 };
 enum : int { SDE_MEAN_PREDICTION = 0, SDE_PARTICLE_FILTER = 1 };
 enum : int { EM_REFERENCE_ADAPTIVE = 0, EM_FIXED_STEP = 1 };

@@ -180,7 +180,7 @@ int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, p
         m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;
         m->m.info_json = m->m.cm.model_info_json();
         std::vector<std::pair<int, std::string>> entries;
-        if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 4; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
+        if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 5; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
         else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
         m->m.source_cache = m->m.cm.cuda_source(entries, false);
         *out = m;
@@ -196,7 +196,7 @@ const char* pharmsol_cuda_model_info_json(const pcu_model* m) { return m->m.info
 const char* pharmsol_cuda_model_cuda_source(const pcu_model* m) { return m->m.source_cache.c_str(); }
 const char* pharmsol_cuda_model_id(const pcu_model* m) { return m->m.cm.id.c_str(); }
 int32_t pharmsol_cuda_model_set_solver(pcu_model* m, int32_t solver, double rtol, double atol) {
-    if (!m || solver < 0 || solver > 3 || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
+    if (!m || solver < 0 || solver > 4 || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
     m->m.opts.solver = solver; m->m.opts.rtol = rtol; m->m.opts.atol = atol;
     return PCU_OK;
 }

@@ -734,6 +734,9 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     // ---- flags -----------------------------------------------------------------------------------------
     const bool dyn_reads_derived = (sc_dyn.deps & DEP_DERIVED) != 0 || (sc_diff.deps & DEP_DERIVED) != 0;
     const bool rhs_uses_cov = (sc_dyn.deps & DEP_COV) || (sc_diff.deps & DEP_COV) || (dyn_reads_derived && (derive_deps & DEP_COV));
+    // explicit time dependence of the right-hand side (t itself or covariates, directly or through derive):
+    // Rosenbrock methods then need the df/dt term
+    const bool rhs_time_dep = (sc_dyn.deps & (DEP_T | DEP_COV)) != 0 || (dyn_reads_derived && (derive_deps & (DEP_T | DEP_COV)) != 0);
     std::ostringstream H;
     H << "    static constexpr int KIND = " << (int)ast.kind << ";\n";
     H << "    static constexpr int NP = " << cm.parameters.size() << ", NCOV = " << cm.covariates.size() << ", NSTATE = " << cm.state_len
@@ -743,7 +746,7 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     H << "    static constexpr bool HAS_DERIVE = " << (cm.has_derive ? "true" : "false") << ", HAS_INIT = " << (cm.has_init ? "true" : "false")
       << ", HAS_LAG = " << (cm.has_lag ? "true" : "false") << ", HAS_FA = " << (cm.has_fa ? "true" : "false") << ";\n";
     H << "    static constexpr bool RHS_USES_COV = " << (rhs_uses_cov ? "true" : "false") << ", RHS_USES_DERIVED = " << (dyn_reads_derived ? "true" : "false")
-      << ", KP_USES_DERIVED = " << (kp_uses_derived ? "true" : "false") << ";\n";
+      << ", KP_USES_DERIVED = " << (kp_uses_derived ? "true" : "false") << ", RHS_TIME_DEP = " << (rhs_time_dep ? "true" : "false") << ";\n";
     cm.struct_body = H.str() + S.str();
     cm.id = fnv1a_hex(cm.struct_body);
     return cm;

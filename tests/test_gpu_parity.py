@@ -118,7 +118,7 @@ def test_corpus_analytical(ps, oracle, case):
 
 
 @pytest.mark.parametrize("case", ["ode", "ode_full"])
-@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2"])
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4"])
 def test_corpus_ode(ps, oracle, case, solver):
     src, twin, p, ops, _ = FX.CORPUS[case]
     tol = 1e-8 if solver == "TrBdf2" else 1e-10
@@ -207,7 +207,7 @@ def test_c2_reference_default_tolerance_agrees_with_oracle_solver(ps, oracle, H,
     assert rel(pred[:offs[1]], want, 1e-3).max() <= 5e-3
 
 
-@pytest.mark.parametrize("solver,tol,bar", [("Sdirk4", 1e-9, 1e-6), ("TrBdf2", 1e-8, 2e-5), ("Dopri5", 1e-10, 1e-6)])
+@pytest.mark.parametrize("solver,tol,bar", [("Sdirk4", 1e-9, 1e-6), ("TrBdf2", 1e-8, 2e-5), ("Dopri5", 1e-10, 1e-6), ("Rodas4", 1e-9, 1e-6)])
 def test_c4_stiff_vs_radau_golden(ps, solver, tol, bar):
     """stiff_c4.json: SciPy Radau rtol=1e-12 predictions (ke0 up to 50 /h)."""
     from benches import workloads
@@ -217,9 +217,10 @@ def test_c4_stiff_vs_radau_golden(ps, solver, tol, bar):
         assert rel(got, c["predictions"], 1e-6).max() <= bar, (solver, c["params"])
 
 
-def test_c4_matrix(ps, oracle, H, W):
+@pytest.mark.parametrize("solver", ["Sdirk4", "Rodas4"])
+def test_c4_matrix(ps, oracle, H, W, solver):
     w = W.make("c4", nsub=8, nspp=96)
-    eq, data, ems, psi = _matrix(ps, H, w, with_solver=(ps.OdeSolver.Sdirk4,), with_tolerances=(1e-9, 1e-9))
+    eq, data, ems, psi = _matrix(ps, H, w, with_solver=(getattr(ps.OdeSolver, solver),), with_tolerances=(1e-9, 1e-9))
     om, od, oe = H.oracle_objects(w, solver="dopri5", rtol=1e-11, atol=1e-12)
     ref = om.log_likelihood_matrix(od, w["support_points"], oe)
     ll_close(psi, ref, 8, 1e-6)
@@ -306,7 +307,7 @@ def test_lag_reorders_events_per_support_point(ps, oracle):
     assert rel(pred, want, 1e-10).max() <= 1e-12
 
 
-@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2"])
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4"])
 def test_ode_infusion_dose_conservation(ps, solver):
     """ode/mod.rs:1274-1344."""
     src = "name = acc\nkind = ode\nparams = ke, v\nstates = central\noutputs = cp\ninfusion(iv) -> central\ndx(central) = -ke * central\nout(cp) = central / v ~ continuous()\n"
@@ -462,3 +463,59 @@ def test_c2_full_size_properties(ps, oracle, H, W):
     assert worst <= 1e-4, worst     # rtol = atol = 1e-6 solver: likelihood amplifies prediction error by |z| pred/sigma
     perm = rng.permutation(20000)[:4096]
     assert np.array_equal(ps.log_likelihood_matrix(eq, data, spp[perm], ems), psi[:, perm])
+
+
+# ---- randomized timelines: every closed-form kernel vs the oracle -----------------------------------------------------------
+def _random_subject(rng, absorb, n_occ):
+    ops = []
+    grid = np.round(rng.uniform(0.0, 48.0, 40) * 4) / 4          # quarter-hour grid -> plenty of exact ties
+    for occ in range(n_occ):
+        if occ:
+            ops.append(("reset",))
+        for _ in range(rng.integers(1, 5)):
+            ops.append(("bolus", float(rng.choice(grid)), float(rng.uniform(10, 500)), "1" if (absorb and rng.random() < 0.4) else "0"))
+        for _ in range(rng.integers(0, 4)):
+            ops.append(("infusion", float(rng.choice(grid)), float(rng.uniform(10, 500)), "0", float(rng.choice([0.25, 0.5, 1.0, 3.0, 7.5]))))
+        for _ in range(rng.integers(1, 12)):
+            t = float(rng.choice(grid))
+            ops.append(("missing_observation", t, "0") if rng.random() < 0.3 else ("observation", t, float(rng.uniform(0.1, 20.0)), "0"))
+    return ops
+
+
+@pytest.mark.parametrize("kernel", list(FX.KERNEL_PARAMS))
+def test_random_timelines_match_oracle(ps, oracle, kernel):
+    """Overlapping infusions, ties between observations / boluses / infusion boundaries, several occasions,
+    missing observations, ragged subjects: predictions <= 1e-12 relative (floor 1e-9 of the largest amount),
+    log-likelihood <= 1e-12 scaled."""
+    seed = sum(kernel.encode()) + 20261018          # deterministic per kernel (hash() is salted per process)
+    rng = np.random.default_rng(seed)
+    absorb = kernel.endswith("with_absorption")
+    subjects = [(f"r{i}", _random_subject(rng, absorb, int(rng.integers(1, 4)))) for i in range(12)]
+    names = FX.KERNEL_PARAMS[kernel]
+    nspp = 64
+
+    def draw(name):
+        if name in ("v", "vc", "vp", "v2", "v3"):
+            return rng.uniform(5.0, 80.0, nspp)
+        if name in ("cl", "q", "q2", "q3"):
+            return rng.uniform(0.5, 20.0, nspp)
+        return rng.uniform(0.02, 2.5, nspp)
+    spp = np.stack([draw(n) for n in names], axis=1)
+    eq = ps.Equation.from_dsl(FX.kernel_dsl(kernel))
+    data = ps.Data([ps.Subject(i, o) for i, o in subjects])
+    em = ("additive", 0.05, (0.1, 0.15, 0.0, 0.0))
+    ems = ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(*em[2]), em[1]))
+    psi = ps.log_likelihood_matrix(eq, data, spp, ems)
+    om = oracle.Model(kernel)
+    od = oracle.Data([oracle.Subject(o, i) for i, o in subjects])
+    ref = om.log_likelihood_matrix(od, spp, oracle.ErrorModels([em]))
+    nobs = max(sum(1 for o in ops if o[0] == "observation") for _, ops in subjects)
+    ll_close(psi, ref, nobs, 1e-11 if kernel.startswith("three") else 1e-12)
+    pred, offs = eq.predictions_matrix(data, spp[:8])
+    for i in range(len(subjects)):
+        for j in range(8):
+            want = om.predictions(od.subjects[i], spp[j])
+            got = pred[offs[i]:offs[i + 1], j]
+            assert got.shape == want.shape
+            floor = 1e-9 * max(1.0, np.max(np.abs(want)))
+            assert rel(got, want, floor).max() <= (2e-11 if kernel.startswith("three") else 1e-12), (kernel, i, j)
