@@ -170,11 +170,20 @@ def events_per_subject(w):
 
 
 # ---------------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(args, w, nsub, budget_s, threads=0):
     """Time the oracle (restated CPU path, OpenMP over subjects) on a bounded sample: all subjects x
     the first S support points, S calibrated so the sample takes ~budget_s.  Returns (pairs/s, info)."""
     from benches import harness as H
     import oracle as O
+    threads = threads or host_cores()
     kw = {}
     if w["kind"] == "ode":
         kw = dict(solver="dopri5", rtol=args.tol, atol=args.tol)

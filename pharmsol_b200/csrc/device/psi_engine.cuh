@@ -234,16 +234,22 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
 template <class M, int SOLVER>
 __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
                                                 long long spp_ld, const RunOpts& opt, const OutView& out) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncols) return;
+    // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
+    // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
+    const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
+    const int nsub = (opt.nsub_limit > 0 && opt.nsub_limit < pop.nsub) ? opt.nsub_limit : pop.nsub;
     Counters cnt;
-    for (int subj = blockIdx.y; subj < pop.nsub; subj += gridDim.y) {
+    for (int subj = blockIdx.y; subj < nsub; subj += gridDim.y) {
         PairCtx<M> c;
 #pragma unroll
         for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
         int status = ST_OK;
         double* pred = (opt.want_pred && out.pred) ? out.pred + j : nullptr;
+        const unsigned int work0 = cnt.steps + cnt.rejected;
         double ll = run_pair<M, SOLVER>(pop, opt, subj, c, status, cnt, pred, out.ld_pred);
+        if (out.col_work) atomicAdd(out.col_work + j, cnt.steps + cnt.rejected - work0);
         if (status != ST_OK) {
             ll = psi_nan();
             report_error(out, (long long)subj + j * (long long)pop.nsub, status);

@@ -122,6 +122,8 @@ struct RunOpts {
     int32_t em_mode;          // EM_*
     int32_t want_pred;        // write per-observation predictions
     int32_t want_ll;          // accumulate the log-likelihood (0 for estimate_predictions: no error model needed)
+    int32_t nsub_limit;       // > 0: only the first nsub_limit subjects (work probe)
+    int32_t balance;          // ODE: order the columns by probed step counts so the lanes of a warp do similar work
 };
 
 // Output buffers.
@@ -134,6 +136,8 @@ struct OutView {
     unsigned long long* counters;      // [0] accepted steps [1] rejected steps [2] rhs/kernel evals [3] Newton iters
     double* scratch;                   // SDE particle workspace: one slab of scratch_stride doubles per CTA
     int64_t scratch_stride;
+    const int32_t* col_perm;           // optional: thread slot q evaluates column col_perm[q] (work-balanced warps)
+    unsigned int* col_work;            // optional (probe launch): per-column solver attempts, atomically accumulated
 };
 
 }  // namespace psi

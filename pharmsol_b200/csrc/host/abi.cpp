@@ -175,6 +175,7 @@ int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, p
         m->m.opts.solver = psi::SOLVER_DOPRI5;
         m->m.opts.cov_time = psi::COVTIME_INTERVAL_END;
         m->m.opts.max_steps = 200000;
+        m->m.opts.balance = 1;
         m->m.opts.nparticles = m->m.cm.particles > 0 ? m->m.cm.particles : 1000;
         m->m.opts.sde_mode = psi::SDE_MEAN_PREDICTION;
         m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;

@@ -364,22 +364,63 @@ ModelAst parse_authoring(const std::string& src) {
     bool explicit_kind = false;
     std::map<std::string, std::pair<ExprP, ExprP>> route_mods;   // route -> (lag, fa)
     std::set<std::string> declared_outputs;
-    size_t off = 0;
-    while (off <= src.size()) {
-        size_t eol = src.find('\n', off);
-        if (eol == std::string::npos) eol = src.size();
-        std::string line = src.substr(off, eol - off);
-        const int base = (int)off;
-        off = eol + 1;
-        const size_t hash = line.find('#');
-        if (hash != std::string::npos) line = line.substr(0, hash);
+    // ---- physical lines -> logical lines (authoring.rs: a statement continues while a `{` / `(` / `[` is open,
+    // and an `else` that starts the next non-trivial line continues an `if`); comments are stripped per
+    // physical line, offsets are kept for diagnostics
+    struct Logical { std::string text; int base; };
+    std::vector<Logical> logical;
+    {
+        std::vector<std::pair<std::string, int>> phys;
+        size_t off0 = 0;
+        while (off0 <= src.size()) {
+            size_t eol = src.find('\n', off0);
+            if (eol == std::string::npos) eol = src.size();
+            std::string line = src.substr(off0, eol - off0);
+            const size_t hash = line.find('#');
+            if (hash != std::string::npos) line = line.substr(0, hash);
+            const size_t sl = line.find("//");
+            if (sl != std::string::npos) line = line.substr(0, sl);
+            phys.emplace_back(line, (int)off0);
+            if (eol == src.size()) break;
+            off0 = eol + 1;
+        }
+        auto starts_with_else = [](const std::string& l) {
+            const std::string t = trim(l);
+            return t.compare(0, 4, "else") == 0 && (t.size() == 4 || !(std::isalnum((unsigned char)t[4]) || t[4] == '_'));
+        };
+        size_t k = 0;
+        while (k < phys.size()) {
+            if (trim(phys[k].first).empty()) { ++k; continue; }
+            Logical L{phys[k].first, phys[k].second};
+            int depth = 0;
+            auto scan = [&](const std::string& l) { for (char c : l) { if (c == '{' || c == '(' || c == '[') ++depth; else if (c == '}' || c == ')' || c == ']') --depth; } };
+            scan(phys[k].first);
+            ++k;
+            while (k < phys.size()) {
+                if (depth > 0) { L.text += "\n" + phys[k].first; scan(phys[k].first); ++k; continue; }
+                size_t nx = k;
+                while (nx < phys.size() && trim(phys[nx].first).empty()) ++nx;
+                if (nx < phys.size() && starts_with_else(phys[nx].first)) {
+                    for (; k <= nx; ++k) { L.text += "\n" + phys[k].first; scan(phys[k].first); }
+                    continue;
+                }
+                break;
+            }
+            logical.push_back(L);
+        }
+    }
+    for (size_t li = 0; li < logical.size(); ++li) {
+        const std::string& line = logical[li].text;
+        const int base = logical[li].base;
+        const size_t eol = 0; (void)eol;
         const std::string t = trim(line);
-        if (t.empty()) { if (eol == src.size()) break; continue; }
+        if (t.empty()) continue;
 
         if (t.compare(0, 2, "if") == 0 && (t.size() == 2 || !(std::isalnum((unsigned char)t[2]) || t[2] == '_'))) {
-            Parser p(lex(t, base, false));
+            Parser p(lex(t, base, true));
             m.derive.push_back(p.parse_stmt());
-            if (eol == src.size()) break;
+            p.skip_nl_only();
+            if (p.peek().kind != Tk::End) throw DslError("unexpected trailing tokens `" + p.peek().text + "` after `if` statement", p.peek().pos);
             continue;
         }
         const size_t arrow = find_top_level(t, "->", false);
@@ -400,7 +441,6 @@ ModelAst parse_authoring(const std::string& src) {
                 if (q.name == r.name && q.kind == r.kind) throw DslError("duplicate route `" + r.name + "`", base);
             parse_place(rhs, base + (int)arrow + 2, r.dest, r.dest_index);
             m.routes.push_back(r);
-            if (eol == src.size()) break;
             continue;
         }
         const size_t eq = find_top_level(t, "=", true);
@@ -477,7 +517,6 @@ ModelAst parse_authoring(const std::string& src) {
             if (declared_outputs.count(lhs)) { s.callee = "out"; m.outputs.push_back(s); }
             else m.derive.push_back(s);
         }
-        if (eol == src.size()) break;
     }
     for (auto& kv : route_mods) {
         bool found = false;

@@ -45,6 +45,7 @@ struct Ctx {
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
     DevBuf spp_rows, spp_soa, out, pred, scratch;
+    DevBuf col_work, col_idx, col_sort;      // work-balanced column order (ODE): probe counts, permutation, cub scratch
     int64_t launches = 0;
     double last_kernel_ms = 0.0;
     unsigned long long last_counters[4] = {0, 0, 0, 0};

@@ -128,3 +128,97 @@ for obs, pred, sigma in [(0, 0, 1), (1.0, 1.0, 0.3), (2.5, 1.0, 0.5), (0.1, 4.0,
     norm.append(dict(obs=obs, pred=pred, sigma=sigma, logpdf=float(logpdf), logcdf=float(mp.log(cdf)), logsf=float(mp.log(sf))))
 json.dump(norm, open(os.path.join(OUT, "normal.json"), "w"), indent=0)
 print("wrote", sorted(os.listdir(OUT)))
+
+# ---- dsl_features.json: a DSL model exercising the front end (array states, constants, statement-level if /
+# else-if, conditional expression, intrinsics, explicit rate(), time-dependent RHS, lag, fa) against an
+# independent SciPy DOP853 integration (rtol 1e-13) of the same equations written by hand --------------------
+DSL_FEATURES = """
+name = dsl_features
+kind = ode
+params = ktr, cl, v, vmax, km, f_oral
+covariates = wt@linear
+const wt_ref = 70.0
+states = depot, transit[3], central
+derived = cl_i, sat, scale
+outputs = cp, lncp
+
+bolus(oral) -> depot
+infusion(iv) -> central
+
+lag(oral) = 0.25
+fa(oral) = min(max(f_oral, 0.0), 1.0)
+
+scale = pow(wt / wt_ref, 0.75)
+if (wt > 80) {
+    cl_i = cl * scale * 1.1
+} else if (wt > 60) {
+    cl_i = cl * scale
+} else {
+    cl_i = cl * scale * 0.9
+}
+sat = if (central / v > 2.0) { vmax * (central / v - 2.0) / (km + central / v) } else { 0.0 }
+
+dx(depot) = -ktr * depot
+dx(transit[0]) = ktr * depot - ktr * transit[0]
+dx(transit[1]) = ktr * (transit[0] - transit[1])
+dx(transit[2]) = ktr * (transit[1] - transit[2])
+dx(central) = ktr * transit[2] - (cl_i / v + sat) * central + rate(iv) * (1 - 0.1 * exp(-t / 4))
+
+out(cp) = central / v ~ continuous()
+out(lncp) = log(abs(central / v) + 1e-9) + sqrt(2 ^ 2) - 2 ~ continuous()
+"""
+
+
+def dsl_features_truth(p, wt0, wt1, doses, infusions, obs):
+    """doses: [(t, amount)] oral; infusions: [(t, amount, dur)]; obs: [(t, outeq)]; wt linear (0, wt0) -> (48, wt1)."""
+    ktr, cl, v, vmax, km, f_oral = p
+    fa = min(max(f_oral, 0.0), 1.0)
+
+    def wt(t):
+        return wt0 + (wt1 - wt0) * min(t, 48.0) / 48.0
+
+    def rhs(t, y, rate):
+        w = wt(t)
+        scale = (w / 70.0) ** 0.75
+        cl_i = cl * scale * (1.1 if w > 80 else 1.0 if w > 60 else 0.9)
+        conc = y[4] / v
+        sat = vmax * (conc - 2.0) / (km + conc) if conc > 2.0 else 0.0
+        return [-ktr * y[0], ktr * y[0] - ktr * y[1], ktr * (y[1] - y[2]), ktr * (y[2] - y[3]),
+                ktr * y[3] - (cl_i / v + sat) * y[4] + rate * (1 - 0.1 * np.exp(-t / 4))]
+    ev = [(t + 0.25, 1, ("bolus", a * fa)) for t, a in doses] + [(t, 0, ("obs", o)) for t, o in obs]
+    bps = sorted({t for t, _, _ in ev} | {b for t, a, d in infusions for b in (t, t + d)})
+    ev.sort(key=lambda e: (e[0], e[1]))
+    y = np.zeros(5)
+    out = []
+    tcur = bps[0]
+    k = 0
+    for b in bps:
+        if b > tcur:
+            rate = sum(a / d for t, a, d in infusions if t <= tcur and b <= t + d)
+            sol = solve_ivp(lambda t, yy: rhs(t, yy, rate), (tcur, b), y, method="DOP853", rtol=1e-13, atol=1e-13)
+            y = sol.y[:, -1]
+            tcur = b
+        while k < len(ev) and ev[k][0] == b:
+            kind, payload = ev[k][2]
+            if kind == "obs":
+                c = y[4] / v
+                out.append(c if payload == "cp" else np.log(abs(c) + 1e-9) + 2.0 - 2.0)
+            else:
+                y[0] += payload
+            k += 1
+    return out
+
+
+feat = []
+for wt0, wt1 in [(85.0, 95.0), (64.0, 76.0), (50.0, 58.0)]:
+    doses = [(0.0, 300.0), (12.0, 200.0), (24.0, 250.0)]
+    infusions = [(6.0, 400.0, 2.0), (30.0, 300.0, 1.5)]
+    obs = [(0.5, "cp"), (1.0, "cp"), (2.0, "lncp"), (4.0, "cp"), (6.5, "cp"), (8.0, "cp"), (12.25, "cp"), (13.0, "lncp"), (20.0, "cp"),
+           (30.5, "cp"), (31.5, "cp"), (36.0, "lncp"), (47.0, "cp")]
+    ops = [("covariate", "wt", 0.0, wt0), ("covariate", "wt", 48.0, wt1)]
+    ops += [("bolus", t, a, "oral") for t, a in doses] + [("infusion", t, a, "iv", d) for t, a, d in infusions]
+    ops += [("missing_observation", t, o) for t, o in obs]
+    for p in [[1.5, 4.0, 30.0, 1.2, 1.5, 0.8], [0.6, 9.0, 55.0, 0.4, 3.0, 1.3], [3.0, 2.0, 20.0, 2.5, 0.7, 0.55]]:
+        feat.append(dict(params=p, ops=ops, predictions=[float(z) for z in dsl_features_truth(p, wt0, wt1, doses, infusions, obs)]))
+json.dump(dict(dsl=DSL_FEATURES, cases=feat), open(os.path.join(OUT, "dsl_features.json"), "w"), indent=0)
+print("wrote dsl_features.json")

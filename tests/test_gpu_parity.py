@@ -519,3 +519,30 @@ def test_random_timelines_match_oracle(ps, oracle, kernel):
             assert got.shape == want.shape
             floor = 1e-9 * max(1.0, np.max(np.abs(want)))
             assert rel(got, want, floor).max() <= (2e-11 if kernel.startswith("three") else 1e-12), (kernel, i, j)
+
+
+def test_work_balanced_column_order_does_not_change_psi(ps, H, W, monkeypatch):
+    """ODE launches probe per-column step counts on a few subjects and evaluate the columns in sorted order
+    (work-balanced warps).  psi must be bit-identical with the balancing switched off."""
+    w = W.make("c2", nsub=64, nspp=2048)
+    eq, data, ems = H.product_objects(w)
+    eq.with_solver(ps.OdeSolver.Dopri5).with_tolerances(1e-6, 1e-6)
+    monkeypatch.setenv("PHARMSOL_B200_BALANCE", "0")
+    plain = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    monkeypatch.setenv("PHARMSOL_B200_BALANCE", "1")
+    balanced = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    assert np.array_equal(plain, balanced)
+    from pharmsol_b200 import _lib
+    assert _lib.context(0).last_counters["steps"] > 0
+
+
+@pytest.mark.parametrize("solver,tol,bar", [("Dopri5", 1e-10, 1e-6), ("Tsit45", 1e-10, 1e-6), ("Rodas4", 1e-9, 2e-6), ("Sdirk4", 1e-9, 2e-6)])
+def test_dsl_feature_model_vs_scipy_golden(ps, solver, tol, bar):
+    """DSL front end -> CUDA C on a model that uses array states, constants, statement-level if / else-if,
+    a conditional expression, intrinsics, explicit rate(), a time-dependent right-hand side (covariate and t),
+    lag and fa, against an independent SciPy DOP853 integration (scripts/gen_golden.py)."""
+    g = golden("dsl_features")
+    eq = ps.Equation.from_dsl(g["dsl"]).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(tol, tol)
+    for c in g["cases"]:
+        got = gpu_predictions(ps, eq, [tuple(o) for o in c["ops"]], c["params"])
+        assert rel(got, c["predictions"], 1e-4).max() <= bar, (solver, c["params"])
