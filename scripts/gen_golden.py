@@ -185,7 +185,11 @@ def dsl_features_truth(p, wt0, wt1, doses, infusions, obs):
         sat = vmax * (conc - 2.0) / (km + conc) if conc > 2.0 else 0.0
         return [-ktr * y[0], ktr * y[0] - ktr * y[1], ktr * (y[1] - y[2]), ktr * (y[2] - y[3]),
                 ktr * y[3] - (cl_i / v + sat) * y[4] + rate * (1 - 0.1 * np.exp(-t / 4))]
-    ev = [(t + 0.25, 1, ("bolus", a * fa)) for t, a in doses] + [(t, 0, ("obs", o)) for t, o in obs]
+    # Reference quirk restated (ode/mod.rs:343-347, 641-687; dsl/native.rs:1286): the ODE solver clock starts at
+    # occasion.initial_time() computed from the UNLAGGED events and the first event is processed without
+    # advancing the clock, so a lagged bolus that is the first event of its occasion lands at t0 (its lag is
+    # effectively ignored); every later bolus is delayed by the lag.
+    ev = [(t + (0.25 if i > 0 else 0.0), 1, ("bolus", a * fa)) for i, (t, a) in enumerate(doses)] + [(t, 0, ("obs", o)) for t, o in obs]
     bps = sorted({t for t, _, _ in ev} | {b for t, a, d in infusions for b in (t, t + d)})
     ev.sort(key=lambda e: (e[0], e[1]))
     y = np.zeros(5)
