@@ -159,10 +159,10 @@ PSI_DEV InfRange occ_infusions(const PopView& pop, int occ) {
     const int a = __ldg(pop.inf_offsets + occ), b = __ldg(pop.inf_offsets + occ + 1);
     return InfRange{pop.infs + a, b - a};
 }
-PSI_DEV void load_inf(const InfRec* r, double& time, double& dur, double& amt, int& input) {
+PSI_DEV void load_inf(const InfRec* r, double& time, double& dur, double& rate, int& input) {
     const double2 td = __ldg(reinterpret_cast<const double2*>(r));
     const double2 ai = __ldg(reinterpret_cast<const double2*>(r) + 1);
-    time = td.x; dur = td.y; amt = ai.x;
+    time = td.x; dur = td.y; rate = ai.x;
     input = (int)(__double_as_longlong(ai.y) & 0xffffffffLL);
 }
 template <int NROUTE>
@@ -179,7 +179,7 @@ PSI_DEV void interval_rates(const InfRange& inf, double cur, double next, double
     for (int i = 0; i < inf.n; ++i) {
         double s, d, a; int input;
         load_inf(inf.p + i, s, d, a, input);
-        if (cur >= s && next <= s + d) add_rate<NROUTE>(rate, input, a / d);
+        if (cur >= s && next <= s + d) add_rate<NROUTE>(rate, input, a);
     }
 }
 // active_route_inputs (dsl/native.rs:2651-2665) == SDE drift rule (sde/mod.rs:124-133):
@@ -191,7 +191,7 @@ PSI_DEV void active_rates(const InfRange& inf, double t, double* rate) {
     for (int i = 0; i < inf.n; ++i) {
         double s, d, a; int input;
         load_inf(inf.p + i, s, d, a, input);
-        if (t >= s && t <= s + d) add_rate<NROUTE>(rate, input, a / d);
+        if (t >= s && t <= s + d) add_rate<NROUTE>(rate, input, a);
     }
 }
 // ODE InfusionSchedule (ode/closure.rs:103-195): right-continuous cumulative rate at `t`
@@ -203,7 +203,7 @@ PSI_DEV void segment_rates(const InfRange& inf, double t, double* rate) {
     for (int i = 0; i < inf.n; ++i) {
         double s, d, a; int input;
         load_inf(inf.p + i, s, d, a, input);
-        if (d > 0.0 && s <= t && t < s + d) add_rate<NROUTE>(rate, input, a / d);
+        if (d > 0.0 && s <= t && t < s + d) add_rate<NROUTE>(rate, input, a);
     }
 }
 

@@ -117,7 +117,11 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
         // ---- ODE solver state -------------------------------------------------------------------
         [[maybe_unused]] OdeState<AtLeast1<NS>::v> st;
         [[maybe_unused]] OdeRhs<M> rhs{c};
-        [[maybe_unused]] int bnd = 0, bnd_end = 0;
+        [[maybe_unused]] int bnd = 0, bnd_end = 0, abc = 0;
+        if constexpr (M::KIND == 1) {
+            abc = __ldg(pop.bnd_offsets + occ);
+            bnd_end = __ldg(pop.bnd_offsets + occ + 1);
+        }
         if constexpr (M::KIND == 0) {
             st.t = __ldg(pop.occ_t0 + occ);
             st.h = -1.0;
@@ -169,20 +173,23 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                 if constexpr (M::KIND == 1) {
                     // Analytical interval (native.rs:1871-1937): split at interior infusion
                     // boundaries, dedup at 1e-12, derive at the sub-interval end, kernel step.
+                    // The reference collects the infusion boundaries strictly inside (te, tn) per call, sorts
+                    // and de-duplicates them at 1e-12 (analytical/mod.rs:311-327); the flattener has already
+                    // sorted the occasion's boundaries, so a per-thread cursor walks them instead of
+                    // rescanning every infusion for every sub-interval.
                     if (te != tn) {
                         double last = te;
+                        while (abc < bnd_end && __ldg(pop.bnds + abc) <= te) ++abc;
                         while (true) {
-                            // smallest candidate c in {boundaries strictly inside (te,tn)} U {tn} with c - last >= 1e-12
-                            double nxt = psi_inf();
-                            for (int i = 0; i < inf.n; ++i) {
-                                double s, dd, a; int input;
-                                load_inf(inf.p + i, s, dd, a, input);
-                                const double f2 = s + dd;
-                                if (s > te && s < tn && s > last && !(fabs(s - last) < 1e-12)) nxt = fmin(nxt, s);
-                                if (f2 > te && f2 < tn && f2 > last && !(fabs(f2 - last) < 1e-12)) nxt = fmin(nxt, f2);
+                            while (abc < bnd_end) {          // drop candidates that the 1e-12 dedup would remove
+                                const double bq = __ldg(pop.bnds + abc);
+                                if (bq <= last || fabs(bq - last) < 1e-12) ++abc; else break;
                             }
-                            if (tn > last && !(fabs(tn - last) < 1e-12)) nxt = fmin(nxt, tn);
-                            if (!(nxt < psi_inf())) break;
+                            double nxt;
+                            const double bq = (abc < bnd_end) ? __ldg(pop.bnds + abc) : psi_inf();
+                            if (bq < tn) { nxt = bq; ++abc; }
+                            else if (tn > last && !(fabs(tn - last) < 1e-12)) nxt = tn;
+                            else break;
                             const double dt = nxt - last;
                             interval_rates<NR>(inf, last, nxt, c.rate);
                             if constexpr (!AK_HOISTED) {
@@ -196,6 +203,7 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                             ak.step(x, dt, c.rate[0]);           // built-in kernels read rateiv[0] only (A.3)
                             cnt.evals++;
                             last = nxt;
+                            if (nxt == tn) break;
                         }
                     }
                 } else if constexpr (M::KIND == 0) {

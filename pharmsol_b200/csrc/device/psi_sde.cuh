@@ -124,7 +124,7 @@ struct SdeStep {
             double s, d, a; int input;
             load_inf(inf.p + i, s, d, a, input);
             const double e = s + d;
-            if (t >= s && t <= e) add_rate<NR>(c.rate, input, a / d);
+            if (t >= s && t <= e) add_rate<NR>(c.rate, input, a);
             if (s > t) until = fmin(until, s);
             if (e >= t) until = fmin(until, e);
         }

@@ -78,7 +78,8 @@ struct __attribute__((aligned(16))) CovSeg {
 
 // One infusion of an occasion (warp-uniform), already label-resolved.
 struct __attribute__((aligned(16))) InfRec {
-    double time, duration, amount;
+    double time, duration, rate;      // rate = amount / duration, divided once on the host (the same IEEE quotient
+                                      // the reference forms per use: analytical/mod.rs:356, sde/mod.rs:130)
     int32_t input;
     int32_t pad;
 };

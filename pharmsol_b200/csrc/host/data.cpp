@@ -189,7 +189,7 @@ FlatPopulation flatten_population(const Data& data, const ModelLabels& labels, c
                         const int idx = resolve_input(labels, ev.label, RouteKind::Infusion);
                         r.a = ev.amount; r.b = ev.duration;
                         r.meta = ev_pack(EV_INFUSION, 0, 0, idx, 0);
-                        InfRec ir{}; ir.time = ev.time; ir.duration = ev.duration; ir.amount = ev.amount; ir.input = idx;
+                        InfRec ir{}; ir.time = ev.time; ir.duration = ev.duration; ir.rate = ev.amount / ev.duration; ir.input = idx;
                         f.infs.push_back(ir);
                         if (ev.duration > 0.0) { bounds.push_back(ev.time); bounds.push_back(ev.time + ev.duration); }   // closure.rs:127-144
                         break;
