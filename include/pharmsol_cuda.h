@@ -86,6 +86,16 @@ typedef struct pcu_error_model {
     double c0, c1, c2, c3;
 } pcu_error_model;
 
+/* ResidualErrorModel for one output equation (data/residual_error.rs:69-139): sigma is computed from the
+ * PREDICTION (parametric algorithms: SAEM, FOCE).  kind: PCU_RESID_*; constant: a; proportional: b;
+ * combined: sqrt(a^2 + b^2 f^2); exponential: sigma = a.  sigma is floored at sqrt(DBL_EPSILON). */
+enum { PCU_RESID_MISSING = 0, PCU_RESID_CONSTANT = 1, PCU_RESID_PROPORTIONAL = 2, PCU_RESID_COMBINED = 3, PCU_RESID_EXPONENTIAL = 4 };
+typedef struct pcu_residual_error_model {
+    int32_t kind;
+    int32_t pad;
+    double a, b;
+} pcu_residual_error_model;
+
 /* ---- library / context -------------------------------------------------------------------------- */
 int32_t pharmsol_cuda_abi_version(void);
 int32_t pharmsol_cuda_device_count(int32_t* n);
@@ -197,6 +207,13 @@ int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* po
 int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
                                          const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                                          double* pred_dev, int64_t ld_pred, double* ll_dev_or_null, int64_t ld_out, void* stream);
+/* log_likelihood_batch (src/simulator/likelihood/mod.rs:119-177): one parameter row per subject
+ *   parameters  host, row-major (nrows x nparams); nrows must equal the number of subjects (else PCU_ERR_OTHER)
+ *   out         host, nsub log-likelihoods; -inf for a subject whose simulation fails or whose output has no model
+ * The population may be created without assay error models (they are not used here). */
+int32_t pharmsol_cuda_log_likelihood_batch(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* parameters,
+                                           int64_t nrows, int32_t nparams, const pcu_residual_error_model* models,
+                                           int32_t n_models, double* out);
 /* psi / log_psi deprecated wrappers (matrix.rs:117-150): exp of the log matrix, on device */
 int32_t pharmsol_cuda_psi(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* support_points, int64_t nspp,
                           int32_t nparams, double* out, int32_t* first_error_code, int64_t* first_error_pair);

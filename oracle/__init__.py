@@ -80,6 +80,8 @@ def lib():
             "orc_log_likelihood": (ci, [vp, vp, dp, ci, vp, C.c_ulonglong, dp]),
             "orc_sde_pf_log_likelihood": (ci, [vp, vp, dp, ci, vp, C.c_ulonglong, dp]),
             "orc_log_likelihood_matrix": (ci, [vp, vp, dp, cl, ci, vp, dp, ci, C.c_ulonglong, ci, lp, dp, lp]),
+            "orc_log_likelihood_batch": (ci, [vp, vp, dp, cl, ci, dp, ci, dp]),
+            "orc_residual_sigma": (d, [ci, d, d, d]), "orc_residual_log_likelihood": (d, [ci, d, d, d, d]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -251,6 +253,27 @@ class Model:
             return out, {"seconds": secs.value, "threads": nthreads or lib().orc_max_threads(),
                          "nsteps": stats[0], "nrej": stats[1], "nrhs": stats[2]}
         return out
+
+
+RESID_KIND = {"constant": 1, "proportional": 2, "combined": 3, "exponential": 4, None: 0}
+
+
+def residual_sigma(model, prediction):
+    return lib().orc_residual_sigma(RESID_KIND[model[0]], float(model[1]), float(model[2]), float(prediction))
+
+
+def residual_log_likelihood(model, observation, prediction):
+    return lib().orc_residual_log_likelihood(RESID_KIND[model[0]], float(model[1]), float(model[2]), float(observation), float(prediction))
+
+
+def log_likelihood_batch(model, data, parameters, residual_models):
+    """likelihood/mod.rs:119-177.  residual_models: list per outeq of None | (kind, a, b)
+    (constant: a; proportional: b; combined: a, b; exponential: sigma in a)."""
+    prm = np.ascontiguousarray(parameters, dtype=np.float64)
+    res = np.array([[RESID_KIND[m[0]], m[1], m[2]] if m else [0, 0, 0] for m in residual_models], dtype=np.float64).reshape(-1)
+    out = np.empty(prm.shape[0], dtype=np.float64)
+    _check(lib().orc_log_likelihood_batch(model.ptr, data.ptr, _dp(prm), prm.shape[0], prm.shape[1], _dp(res), len(residual_models), _dp(out)))
+    return out
 
 
 def lognormpdf(o, p, s):

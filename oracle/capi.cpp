@@ -138,6 +138,39 @@ int orc_sde_pf_log_likelihood(void* model, void* subject, const double* p, int n
     catch (const std::exception& e) { g_last_error = e.what(); return OtherError; }
 }
 
+double orc_residual_sigma(int kind, double a, double b, double prediction) {
+    ResidualErrorModel r; r.kind = (ResidualErrorModel::Kind)kind; r.a = a; r.b = b; return r.sigma(prediction);
+}
+double orc_residual_log_likelihood(int kind, double a, double b, double observation, double prediction) {
+    ResidualErrorModel r; r.kind = (ResidualErrorModel::Kind)kind; r.a = a; r.b = b; return r.log_likelihood(observation, prediction);
+}
+// ---- log_likelihood_batch: likelihood/mod.rs:119-177 ------------------------------------------------
+// params: row-major (nsub x np), one row per subject.  resid: nres x {kind, a, b}.  out[nsub];
+// a subject whose simulation fails scores -inf (mod.rs:134-137).
+int orc_log_likelihood_batch(void* model, void* data, const double* params, long nrows, int np, const double* resid, int nres,
+                             double* out) {
+    const Model& m = *(Model*)model;
+    const Data& d = *(Data*)data;
+    if (nrows != (long)d.subjects.size()) {
+        g_last_error = "parameters has " + std::to_string(nrows) + " rows but there are " + std::to_string(d.subjects.size()) + " subjects";
+        return OtherError;
+    }
+    ResidualErrorModels rem;
+    for (int k = 0; k < nres; ++k) {
+        ResidualErrorModel r; r.kind = (ResidualErrorModel::Kind)(int)resid[3 * k]; r.a = resid[3 * k + 1]; r.b = resid[3 * k + 2];
+        rem.models.push_back(r);
+    }
+    for (long i = 0; i < nrows; ++i) {
+        try {
+            auto preds = estimate_predictions(m, d.subjects[(size_t)i], V(params + i * np, params + (i + 1) * np), 0, nullptr);
+            std::vector<std::pair<size_t, std::pair<double, double>>> rows;
+            for (const auto& p : preds) if (p.has_obs) rows.push_back({p.outeq, {p.observation, p.prediction}});
+            out[i] = rem.total(rows);
+        } catch (const std::exception&) { out[i] = -std::numeric_limits<double>::infinity(); }
+    }
+    return 0;
+}
+
 // ---- psi matrix: likelihood/matrix.rs:52-106 ----------------------------------------------------
 // spp: row-major (nspp x np).  out: column-major (nsub x nspp).  sde_mode: 0 = mean prediction
 // (what log_likelihood_matrix does), 1 = particle filter.  Returns 0 or the first error's code;

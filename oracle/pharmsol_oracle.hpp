@@ -324,6 +324,42 @@ struct Prediction {                      // likelihood/prediction.rs:18-27
 
 constexpr double LOG_2PI = 1.8378770664093453;   // distributions.rs:12
 
+// ---------------------------------------------------------------------------------------------
+// ResidualErrorModel(s): prediction-based sigma for parametric algorithms — data/residual_error.rs:69-426
+// ---------------------------------------------------------------------------------------------
+struct ResidualErrorModel {
+    enum Kind { Missing = 0, Constant = 1, Proportional = 2, Combined = 3, Exponential = 4 } kind = Missing;
+    double a = 0.0, b = 0.0;     // Constant{a} | Proportional{b} | Combined{a,b} | Exponential{sigma = a}
+    double sigma(double prediction) const {                       // residual_error.rs:178-197
+        double raw = 0.0;
+        switch (kind) {
+            case Constant: raw = a; break;
+            case Proportional: raw = b * std::fabs(prediction); break;
+            case Combined: raw = std::sqrt(a * a + (b * b) * (prediction * prediction)); break;
+            case Exponential: raw = a; break;
+            default: break;
+        }
+        return std::fmax(raw, std::sqrt(std::numeric_limits<double>::epsilon()));
+    }
+    double log_likelihood(double observation, double prediction) const {   // residual_error.rs:265-271
+        const double s = sigma(prediction);
+        const double nr = (observation - prediction) / s;
+        return -0.5 * (std::log(6.283185307179586476925286766559) + 2.0 * std::log(s) + nr * nr);
+    }
+};
+struct ResidualErrorModels {
+    std::vector<ResidualErrorModel> models;     // indexed by outeq; Missing = no model
+    // residual_error.rs:413-426: missing model for an outeq => -inf
+    double total(const std::vector<std::pair<size_t, std::pair<double, double>>>& outeq_obs_pred) const {
+        double t = 0.0;
+        for (const auto& r : outeq_obs_pred) {
+            if (r.first >= models.size() || models[r.first].kind == ResidualErrorModel::Missing) return -std::numeric_limits<double>::infinity();
+            t += models[r.first].log_likelihood(r.second.first, r.second.second);
+        }
+        return t;
+    }
+};
+
 // distributions.rs:31-34
 inline double lognormpdf(double obs, double pred, double sigma) {
     double diff = obs - pred;

@@ -33,6 +33,10 @@ class PharmsolError(RuntimeError):
         super().__init__(f"{self.variant}: {message}" if message else self.variant)
 
 
+class pcu_residual_error_model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
 class pcu_error_model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("factor", C.c_double),
                 ("c0", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("c3", C.c_double)]
@@ -119,6 +123,7 @@ def lib():
         "pharmsol_cuda_predictions": (i32, [vp, vp, vp, dp, i64, i32, dp]),
         "pharmsol_cuda_predictions_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, i64, vp]),
         "pharmsol_cuda_psi": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
+        "pharmsol_cuda_log_likelihood_batch": (i32, [vp, vp, vp, dp, i64, i32, P(pcu_residual_error_model), i32, dp]),
         "pharmsol_cuda_measure_fp64_peak": (i32, [vp, dp, dp]),
     }
     for name, (res, args) in sig.items():
@@ -418,3 +423,19 @@ def pinned_array(shape, order="C"):
     buf = (C.c_double * max(n, 1)).from_address(ptr)
     arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
     return arr, ptr
+
+
+def log_likelihood_batch(ctx, model, pop, parameters, residual_models):
+    """likelihood/mod.rs:119-177: one parameter row per subject -> nsub log-likelihoods.
+    residual_models: list per outeq of None | (kind:int, a, b)."""
+    prm = np.ascontiguousarray(parameters, dtype=np.float64)
+    if prm.ndim != 2:
+        raise PharmsolError(66, "parameters must be 2-D (rows = subjects)")
+    n = len(residual_models)
+    arr = (pcu_residual_error_model * max(n, 1))()
+    for k, m in enumerate(residual_models):
+        if m is not None:
+            arr[k].kind, arr[k].a, arr[k].b = int(m[0]), float(m[1]), float(m[2])
+    out = np.empty(pop.nsubjects, dtype=np.float64)
+    check(lib().pharmsol_cuda_log_likelihood_batch(ctx.ptr, model.ptr, pop.ptr, _dp(prm), prm.shape[0], prm.shape[1], arr, n, _dp(out)))
+    return out

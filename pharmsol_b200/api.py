@@ -488,6 +488,56 @@ def psi(equation, subjects, support_points, error_models, progress=False):
     return equation.log_likelihood_matrix(subjects, np.asarray(support_points, dtype=np.float64), error_models, exponentiate=True)
 
 
+class ResidualErrorModel:
+    """data/residual_error.rs:69-139: sigma from the PREDICTION (parametric algorithms)."""
+    CONSTANT, PROPORTIONAL, COMBINED, EXPONENTIAL = 1, 2, 3, 4
+
+    def __init__(self, kind, a=0.0, b=0.0):
+        self.kind, self.a, self.b = int(kind), float(a), float(b)
+
+    @classmethod
+    def constant(cls, a):
+        return cls(cls.CONSTANT, a, 0.0)
+
+    @classmethod
+    def proportional(cls, b):
+        return cls(cls.PROPORTIONAL, 0.0, b)
+
+    @classmethod
+    def combined(cls, a, b):
+        return cls(cls.COMBINED, a, b)
+
+    @classmethod
+    def exponential(cls, sigma):
+        return cls(cls.EXPONENTIAL, sigma, 0.0)
+
+
+class ResidualErrorModels:
+    """data/residual_error.rs:341-426: keyed by output-equation index."""
+
+    def __init__(self):
+        self.models = {}
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    def add(self, outeq, model):
+        self.models[int(outeq)] = model
+        return self
+
+    def dense(self):
+        n = max(self.models) + 1 if self.models else 0
+        return [((m.kind, m.a, m.b) if (m := self.models.get(k)) is not None else None) for k in range(n)]
+
+
+def log_likelihood_batch(equation: Equation, subjects: Data, parameters, residual_error_models: ResidualErrorModels):
+    """likelihood/mod.rs:119-177: per-subject individual parameters (row i <-> subject i), prediction-based sigma.
+    Returns N log-likelihoods; -inf where the simulation fails or an output has no residual model."""
+    pop = equation.population(subjects, None)
+    return _lib.log_likelihood_batch(equation._ctx(), equation._model, pop, parameters, residual_error_models.dense())
+
+
 class ParameterOrder:
     """parameter_order.rs: validate an external column order once, then permute support-point
     matrices into model order."""

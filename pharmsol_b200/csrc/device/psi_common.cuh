@@ -148,6 +148,24 @@ PSI_DEV double obs_log_likelihood(const EventRec& e, double pred, int& status) {
     return ll;
 }
 
+// ResidualErrorModels::log_likelihood (data/residual_error.rs:178-197, 265-271, 399-426):
+// sigma from the PREDICTION with the sqrt(eps) cutoff; a missing model scores -inf.
+PSI_DEV double resid_log_likelihood(const RunOpts& opt, int outeq, double obs, double pred) {
+    int kind = RESID_MISSING;
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < PSI_MAX_RESID; ++k)
+        if (k == outeq && k < opt.nresid) { kind = opt.resid[k].kind; a = opt.resid[k].a; b = opt.resid[k].b; }
+    if (kind == RESID_MISSING) return -psi_inf();
+    double raw;
+    if (kind == RESID_PROPORTIONAL) raw = b * fabs(pred);
+    else if (kind == RESID_COMBINED) raw = sqrt(a * a + (b * b) * (pred * pred));
+    else raw = a;
+    const double sigma = fmax(raw, 1.4901161193847656e-08);     // f64::EPSILON.sqrt()
+    const double nr = (obs - pred) / sigma;
+    return -0.5 * (1.8378770664093453 + 2.0 * log(sigma) + nr * nr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Infusion helpers (warp-uniform data).
 // ---------------------------------------------------------------------------------------------

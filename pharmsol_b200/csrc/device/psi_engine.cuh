@@ -163,7 +163,10 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                 M::outputs(te, x, c.p, c.cov, c.rate, c.d, y);
                 const double yp = pick<AtLeast1<M::NOUT>::v>(y, ev_index(e.meta));
                 if (pred && e.obs_row >= 0) pred[(long long)e.obs_row * pred_ld] = yp;
-                if (opt.want_ll && ev_has_value(e.meta)) ll += obs_log_likelihood(e, yp, status);
+                if (opt.want_ll && ev_has_value(e.meta)) {
+                    if (opt.diagonal) ll += resid_log_likelihood(opt, ev_index(e.meta), e.a, yp);
+                    else ll += obs_log_likelihood(e, yp, status);
+                }
             }
             // ---- advance to the next event ------------------------------------------------------
             EventRec en;
@@ -249,6 +252,18 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
     const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
     const int nsub = (opt.nsub_limit > 0 && opt.nsub_limit < pop.nsub) ? opt.nsub_limit : pop.nsub;
     Counters cnt;
+    if (opt.diagonal) {
+        // log_likelihood_batch: subject q with parameter row q; a failed simulation scores -inf (mod.rs:134-137)
+        PairCtx<M> c;
+#pragma unroll
+        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + q);
+        int status = ST_OK;
+        double ll = run_pair<M, SOLVER>(pop, opt, (int)q, c, status, cnt, nullptr, 0);
+        if (status != ST_OK) ll = -psi_inf();
+        if (out.ll) out.ll[q] = ll;
+        flush_counters(out, cnt);
+        return;
+    }
     for (int subj = blockIdx.y; subj < nsub; subj += gridDim.y) {
         PairCtx<M> c;
 #pragma unroll

@@ -110,6 +110,15 @@ enum : int { COVTIME_INTERVAL_END = 0, COVTIME_INTERVAL_LENGTH = 1 };
 enum : int { SDE_MEAN_PREDICTION = 0, SDE_PARTICLE_FILTER = 1 };
 enum : int { EM_REFERENCE_ADAPTIVE = 0, EM_FIXED_STEP = 1 };
 
+// ResidualErrorModel (data/residual_error.rs:69-139): prediction-based sigma, evaluated on the device.
+enum : int { RESID_MISSING = 0, RESID_CONSTANT = 1, RESID_PROPORTIONAL = 2, RESID_COMBINED = 3, RESID_EXPONENTIAL = 4 };
+struct ResidErr {
+    int32_t kind;
+    int32_t pad;
+    double a, b;       // Constant{a} | Proportional{b} | Combined{a, b} | Exponential{sigma = a}
+};
+constexpr int PSI_MAX_RESID = 8;
+
 struct RunOpts {
     double rtol, atol;        // ODE tolerances (reference default 1e-4 / 1e-4, ode/mod.rs:40-41)
     double h0;                // initial step (<= 0: automatic)
@@ -125,6 +134,11 @@ struct RunOpts {
     int32_t want_ll;          // accumulate the log-likelihood (0 for estimate_predictions: no error model needed)
     int32_t nsub_limit;       // > 0: only the first nsub_limit subjects (work probe)
     int32_t balance;          // ODE: order the columns by probed step counts so the lanes of a warp do similar work
+    // log_likelihood_batch (likelihood/mod.rs:119-177): thread q evaluates subject q with parameter row q and
+    // scores it with the prediction-based residual error models below
+    int32_t diagonal;
+    int32_t nresid;
+    ResidErr resid[PSI_MAX_RESID];
 };
 
 // Output buffers.

@@ -394,6 +394,46 @@ int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* po
     });
 }
 
+int32_t pharmsol_cuda_log_likelihood_batch(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* params, int64_t nrows, int32_t np,
+                                           const pcu_residual_error_model* models, int32_t n_models, double* out) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !params || !out || nrows < 0 || n_models < 0 || (n_models > 0 && !models)) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        const int64_t nsub = pop->p.flat.nsub;
+        if (nrows != nsub)      // likelihood/mod.rs:128-134
+            throw PharmsolError(PCU_ERR_OTHER, "parameters has " + std::to_string(nrows) + " rows but there are " + std::to_string(nsub) + " subjects");
+        if (np != (int32_t)m->m.cm.parameters.size())
+            throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
+                                                   " parameter value(s), got " + std::to_string(np));
+        if (m->m.cm.kind == dsl::ModelKind::Sde) throw PharmsolError(PCU_ERR_OTHER, "log_likelihood_batch is not available for SDE models on the device");
+        if (n_models > psi::PSI_MAX_RESID) throw PharmsolError(PCU_ERR_OTHER, "at most " + std::to_string(psi::PSI_MAX_RESID) + " residual error models");
+        if (nsub == 0) return (int32_t)PCU_OK;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        Ctx& c = ctx->c;
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        psi::RunOpts opt = m->m.opts;
+        opt.diagonal = 1;
+        opt.nresid = n_models;
+        for (int k = 0; k < psi::PSI_MAX_RESID; ++k) {
+            opt.resid[k].kind = k < n_models ? models[k].kind : psi::RESID_MISSING;
+            opt.resid[k].pad = 0;
+            opt.resid[k].a = k < n_models ? models[k].a : 0.0;
+            opt.resid[k].b = k < n_models ? models[k].b : 0.0;
+        }
+        c.spp_rows.reserve((size_t)nsub * np * 8);
+        c.spp_soa.reserve((size_t)nsub * np * 8);
+        c.out.reserve((size_t)nsub * 8);
+        cuda_check(cudaMemcpyAsync(c.spp_rows.p, params, (size_t)nsub * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D parameters");
+        launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nsub, np, nsub, c.stream);
+        c.launches += 1;
+        launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nsub, nsub, c.out.as<double>(), nsub, nullptr, 0, 0, c.stream, &opt);
+        cuda_check(cudaMemcpyAsync(out, c.out.p, (size_t)nsub * 8, cudaMemcpyDeviceToHost, c.stream), "D2H log-likelihoods");
+        cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+        int32_t code = 0; int64_t pair = -1;
+        collect(c, &code, &pair);      // failures are -inf entries, never an error (mod.rs:134-137)
+        return (int32_t)PCU_OK;
+    });
+}
+
 int32_t pharmsol_cuda_measure_fp64_peak(pcu_ctx* ctx, double* tflops, double* clock_mhz) {
     return guarded([&] {
         if (!ctx || !tflops) return (int32_t)PCU_ERR_INVALID_ARGUMENT;

@@ -547,3 +547,39 @@ def test_dsl_feature_model_vs_scipy_golden(ps, solver, tol, bar):
         got = gpu_predictions(ps, eq, [tuple(o) for o in c["ops"]], c["params"])
         err = rel(got, c["predictions"], 1e-4).max()
         assert err <= bar, (solver, c["params"], err)     # SDIRK4: the simplified-Newton stopping rule limits it to ~1e-5 here
+
+
+# ---- log_likelihood_batch + ResidualErrorModels -----------------------------------------------------
+@pytest.mark.parametrize("name,tol", [("c1", 1e-12), ("c2", 1e-6)])
+def test_log_likelihood_batch_vs_oracle(ps, oracle, H, W, name, tol):
+    """likelihood/mod.rs:119-177: subject i with parameter row i, prediction-based sigma (data/residual_error.rs)."""
+    w = W.make(name, nsub=97, nspp=97)
+    eq, data, _ = H.product_objects(w)
+    okw = {}
+    if name == "c2":
+        eq.with_solver(ps.OdeSolver.Dopri5).with_tolerances(1e-10, 1e-10)
+        okw = dict(solver="dopri5", rtol=1e-12, atol=1e-12)
+    om, od, _ = H.oracle_objects(w, **okw)
+    prm = w["support_points"]
+    for model, omodel in [(ps.ResidualErrorModel.constant(0.5), ("constant", 0.5, 0.0)),
+                          (ps.ResidualErrorModel.proportional(0.15), ("proportional", 0.0, 0.15)),
+                          (ps.ResidualErrorModel.combined(0.1, 0.2), ("combined", 0.1, 0.2)),
+                          (ps.ResidualErrorModel.exponential(0.3), ("exponential", 0.3, 0.0))]:
+        got = ps.log_likelihood_batch(eq, data, prm, ps.ResidualErrorModels().add(0, model))
+        want = oracle.log_likelihood_batch(om, od, prm, [omodel])
+        assert got.shape == (97,) and np.all(np.isfinite(got))
+        assert np.max(np.abs(got - want) / (np.abs(want) + 12)) <= tol
+    # no model for the output -> -inf for everyone; wrong row count -> error (mod.rs:128-134)
+    assert np.all(np.isneginf(ps.log_likelihood_batch(eq, data, prm, ps.ResidualErrorModels())))
+    with pytest.raises(ps.PharmsolError) as e:
+        ps.log_likelihood_batch(eq, data, prm[:5], ps.ResidualErrorModels().add(0, ps.ResidualErrorModel.constant(1.0)))
+    assert "rows but there are 97 subjects" in str(e.value)
+
+
+def test_log_likelihood_batch_failed_simulation_is_neg_inf(ps):
+    eq = ps.Equation.from_dsl(FX.kernel_dsl("two_compartments"))
+    ops = [("bolus", 0.0, 100.0, "0"), ("observation", 1.0, 50.0, "0")]
+    data = ps.Data([ps.Subject("a", ops), ps.Subject("b", ops)])
+    prm = np.array([[0.1, 3.0, 1.0, 1.0], [1.0, -3.0, 1.5, 1.0]])      # second row: imaginary roots
+    out = ps.log_likelihood_batch(eq, data, prm, ps.ResidualErrorModels().add(0, ps.ResidualErrorModel.constant(1.0)))
+    assert np.isfinite(out[0]) and np.isneginf(out[1])

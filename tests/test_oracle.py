@@ -218,3 +218,32 @@ def test_imaginary_roots_is_an_error(oracle):
     with pytest.raises(oracle.OracleError) as e:
         oracle.kernel_step("two_compartments", [1.0, 0.0], [1.0, -3.0, 1.5], 1.0, 0.0)
     assert e.value.code == 12
+
+
+def test_residual_error_model_anchors(oracle):
+    # data/residual_error.rs:450-517
+    c, p, cb = ("constant", 0.5, 0.0), ("proportional", 0.0, 0.1), ("combined", 0.5, 0.1)
+    for pred in (0.0, 100.0, -50.0):
+        assert abs(oracle.residual_sigma(c, pred) - 0.5) < 1e-10
+    assert abs(oracle.residual_sigma(p, 100.0) - 10.0) < 1e-10 and abs(oracle.residual_sigma(p, -100.0) - 10.0) < 1e-10
+    assert abs(oracle.residual_sigma(p, 50.0) - 5.0) < 1e-10
+    assert abs(oracle.residual_sigma(cb, 0.0) - 0.5) < 1e-10 and abs(oracle.residual_sigma(cb, 100.0) - math.sqrt(100.25)) < 1e-10
+    assert oracle.residual_sigma(p, 0.0) >= math.sqrt(2.220446049250313e-16) > 0.0          # sigma cutoff
+    assert abs(oracle.residual_log_likelihood(("constant", 1.0, 0.0), 1.0, 0.0) - (-0.5 * (math.log(2 * math.pi) + 1.0))) < 1e-10
+
+
+def test_log_likelihood_batch_semantics(oracle):
+    # likelihood/mod.rs:119-177: one parameter row per subject; wrong row count is an error; a missing model is -inf
+    m = oracle.Model("one_cpt_iv")
+    subs = [oracle.Subject([("infusion", 0.0, 500.0, "iv", 0.5), ("observation", 1.0, 3.0, "cp"), ("missing_observation", 2.0, "cp"),
+                            ("observation", 4.0, 1.5, "cp")]) for _ in range(3)]
+    d = oracle.Data(subs)
+    prm = [[0.3, 100.0], [0.2, 80.0], [0.5, 150.0]]
+    out = oracle.log_likelihood_batch(m, d, prm, [("combined", 0.1, 0.15)])
+    for i, p in enumerate(prm):
+        pr = m.predictions(subs[i], p)
+        want = sum(oracle.residual_log_likelihood(("combined", 0.1, 0.15), o, f) for o, f in ((3.0, pr[0]), (1.5, pr[2])))
+        assert out[i] == pytest.approx(want, rel=1e-14)
+    assert np.all(np.isneginf(oracle.log_likelihood_batch(m, d, prm, [None])))
+    with pytest.raises(oracle.OracleError):
+        oracle.log_likelihood_batch(m, d, prm[:2], [("constant", 1.0, 0.0)])
