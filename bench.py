@@ -330,7 +330,14 @@ def run_product(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 8.0 * npairs_rank + 8.0 * job.nparams * job.ncols
-    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+    traffic = None
+    try:    # measured DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), scaled per pair where the capture was a sample
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tj:
+            traffic = tj["per_pair"] * npairs_rank if "per_pair" in tj else (tj["bytes"] if (nsub, nspp_per_gpu) == (cfg["nsub"], cfg["nspp"]) else None)
+    except Exception:
+        traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": "measured in this run: register-resident DFMA chains on all SMs (MEASURED_PEAKS.json carries no FP64 figure)",
                 "kernel": "psi_entry_<model>_s<solver> (one thread per pair)", "kernel_ms": kernel_ms_avg,
                 "algorithmic_flops_per_launch": flops, "flops_per_pair": flops / max(npairs_rank, 1),

@@ -132,6 +132,15 @@ void pharmsol_subject_free(pcu_subject* s);
 pcu_data* pharmsol_data_new(void);                                      /* Data::new (data/structs.rs:38) */
 int32_t pharmsol_data_add_subject(pcu_data* d, const pcu_subject* s);   /* copies */
 int64_t pharmsol_data_len(const pcu_data* d);
+/* read_pmetrics (src/data/parser/pmetrics/mod.rs:164-239, row.rs:269-381, 593-672): Pmetrics CSV -> Data.
+ * ID / EVID / TIME required; DUR DOSE ADDL II INPUT OUT OUTEQ CENS C0..C3 optional; every other column is a
+ * covariate (`name!` = carry-forward); ADDL/II doses are expanded, EVID = 4 starts a new occasion,
+ * OUT = -99 is a missing observation.  Errors: PCU_ERR_OTHER with the message in last_error_message. */
+int32_t pharmsol_data_read_pmetrics(const char* path, pcu_data** out);
+int32_t pharmsol_data_from_pmetrics_text(const char* text, size_t len, pcu_data** out);
+/* JSON description (subjects -> occasions -> events, covariates) for inspection; returns the number of bytes
+ * needed (excluding the terminator) and writes at most cap - 1 bytes + NUL into buf (buf may be NULL). */
+int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap);
 void pharmsol_data_free(pcu_data* d);
 
 /* ---- models ----------------------------------------------------------------------------------------- */

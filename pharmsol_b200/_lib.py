@@ -94,6 +94,9 @@ def lib():
         "pharmsol_data_add_subject": (i32, [vp, vp]),
         "pharmsol_data_len": (i64, [vp]),
         "pharmsol_data_free": (None, [vp]),
+        "pharmsol_data_read_pmetrics": (i32, [cs, P(vp)]),
+        "pharmsol_data_from_pmetrics_text": (i32, [cs, sz, P(vp)]),
+        "pharmsol_data_describe_json": (i64, [vp, C.c_char_p, sz]),
         "pharmsol_cuda_model_from_dsl": (i32, [vp, cs, sz, P(vp)]),
         "pharmsol_cuda_model_destroy": (None, [vp]),
         "pharmsol_cuda_model_kind": (i32, [vp]),
@@ -252,12 +255,32 @@ class NativeSubject:
 
 
 class NativeData:
-    def __init__(self, subjects):
+    def __init__(self, subjects=None, ptr=None):
         L = lib()
+        if ptr is not None:
+            self.ptr = ptr
+            return
         self.ptr = C.c_void_p(L.pharmsol_data_new())
         for s in subjects:
             ns = NativeSubject(s.id, s.ops)
             check(L.pharmsol_data_add_subject(self.ptr, ns.ptr))
+
+    @classmethod
+    def from_pmetrics(cls, path=None, text=None):
+        ptr = C.c_void_p()
+        if text is not None:
+            raw = text.encode() if isinstance(text, str) else bytes(text)
+            check(lib().pharmsol_data_from_pmetrics_text(raw, len(raw), C.byref(ptr)))
+        else:
+            check(lib().pharmsol_data_read_pmetrics(_b(path), C.byref(ptr)))
+        return cls(ptr=ptr)
+
+    def describe(self):
+        import json
+        n = lib().pharmsol_data_describe_json(self.ptr, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().pharmsol_data_describe_json(self.ptr, buf, n + 1)
+        return json.loads(buf.value.decode())
 
     def __len__(self):
         return lib().pharmsol_data_len(self.ptr)

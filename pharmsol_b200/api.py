@@ -128,6 +128,40 @@ class Data:
             self._native = _lib.NativeData(self.subjects)
         return self._native
 
+    @classmethod
+    def from_pmetrics(cls, path=None, text=None):
+        """read_pmetrics (data/parser/pmetrics/mod.rs:164-239): the CSV is parsed natively (C++), ADDL/II expanded,
+        occasions split at EVID=4; ``subjects`` mirrors the parsed result as builder ops."""
+        native = _lib.NativeData.from_pmetrics(path=path, text=text)
+        subjects = []
+        cens = {0: Censor.NONE, 1: Censor.BLOQ, 2: Censor.ALOQ}
+        for s in native.describe():
+            ops, fixed = [], []
+            for k, occ in enumerate(s["occasions"]):
+                if k:
+                    ops.append(("reset",))
+                for name, cov in occ["covariates"].items():
+                    ops += [("covariate", name, float(t), float(v)) for t, v in cov["observations"]]
+                    if cov["fixed"]:
+                        fixed.append(("covariate_fixed", k, name, True))
+                for e in occ["events"]:
+                    if e["kind"] == "bolus":
+                        ops.append(("bolus", e["time"], e["amount"], e["label"]))
+                    elif e["kind"] == "infusion":
+                        ops.append(("infusion", e["time"], e["amount"], e["label"], e["duration"]))
+                    elif e["value"] is None:
+                        ops.append(("missing_observation", e["time"], e["label"]))
+                    elif "errorpoly" in e:
+                        ops.append(("observation_with_error", e["time"], e["value"], e["label"], tuple(e["errorpoly"]), cens[e["censoring"]]))
+                    elif e["censoring"]:
+                        ops.append(("censored_observation", e["time"], e["value"], e["label"], cens[e["censoring"]]))
+                    else:
+                        ops.append(("observation", e["time"], e["value"], e["label"]))
+            subjects.append(Subject(s["id"], ops + fixed))
+        data = cls(subjects)
+        data._native = native
+        return data
+
 
 class AssayErrorModel:
     NONE, ADDITIVE, PROPORTIONAL = 0, 1, 2
@@ -536,6 +570,11 @@ def log_likelihood_batch(equation: Equation, subjects: Data, parameters, residua
     Returns N log-likelihoods; -inf where the simulation fails or an output has no residual model."""
     pop = equation.population(subjects, None)
     return _lib.log_likelihood_batch(equation._ctx(), equation._model, pop, parameters, residual_error_models.dense())
+
+
+def read_pmetrics(path):
+    """pharmsol::prelude::data::read_pmetrics."""
+    return Data.from_pmetrics(path=path)
 
 
 class ParameterOrder:

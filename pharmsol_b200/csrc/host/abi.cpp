@@ -158,6 +158,34 @@ int32_t pharmsol_data_add_subject(pcu_data* d, const pcu_subject* s) {
 }
 int64_t pharmsol_data_len(const pcu_data* d) { return d ? (int64_t)d->d.subjects.size() : 0; }
 void pharmsol_data_free(pcu_data* d) { delete d; }
+int32_t pharmsol_data_read_pmetrics(const char* path, pcu_data** out) {
+    return guarded([&] {
+        if (!path || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        auto* d = new pcu_data();
+        try { d->d = read_pmetrics_file(path); } catch (...) { delete d; throw; }
+        *out = d;
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_data_from_pmetrics_text(const char* text, size_t len, pcu_data** out) {
+    return guarded([&] {
+        if (!text || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        auto* d = new pcu_data();
+        try { d->d = read_pmetrics_text(std::string(text, len)); } catch (...) { delete d; throw; }
+        *out = d;
+        return (int32_t)PCU_OK;
+    });
+}
+int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap) {
+    if (!d) return -1;
+    const std::string s = describe_data_json(d->d);
+    if (buf && cap > 0) {
+        const size_t n = std::min(cap - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = '\0';
+    }
+    return (int64_t)s.size();
+}
 
 // ---- models ----------------------------------------------------------------------------------------------
 int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, pcu_model** out) {

@@ -88,6 +88,11 @@ struct Data {
     std::vector<Subject> subjects;
 };
 
+// Pmetrics CSV -> Data (data/parser/pmetrics/{mod.rs, row.rs}); throws PharmsolError(ST_OTHER, message)
+Data read_pmetrics_text(const std::string& text);
+Data read_pmetrics_file(const std::string& path);
+std::string describe_data_json(const Data& d);
+
 enum class ErrKind : int { None = 0, Additive = 1, Proportional = 2 };
 struct AssayErrorModel {
     ErrKind kind = ErrKind::None;
