@@ -583,3 +583,56 @@ def test_log_likelihood_batch_failed_simulation_is_neg_inf(ps):
     prm = np.array([[0.1, 3.0, 1.0, 1.0], [1.0, -3.0, 1.5, 1.0]])      # second row: imaginary roots
     out = ps.log_likelihood_batch(eq, data, prm, ps.ResidualErrorModels().add(0, ps.ResidualErrorModel.constant(1.0)))
     assert np.isfinite(out[0]) and np.isneginf(out[1])
+
+
+def test_c3_full_shard_properties(ps, oracle, H, W):
+    """C3 at the per-GPU shard of BASELINE configs[2] (10,000 subjects x 6,250 support points): finite, spot-checked
+    against the oracle, bit-exact under column permutation and subject subsetting."""
+    w = W.make("c3", nsub=10000, nspp=6250)
+    eq, data, ems = H.product_objects(w)
+    spp = w["support_points"]
+    psi = ps.log_likelihood_matrix(eq, data, spp, ems)
+    assert psi.shape == (10000, 6250) and np.all(np.isfinite(psi))
+    om, od, oe = H.oracle_objects(w)
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for i, j in zip(rng.integers(0, 10000, 200), rng.integers(0, 6250, 200)):
+        want = om.log_likelihood(od.subjects[i], spp[j], oe)
+        worst = max(worst, abs(psi[i, j] - want) / (abs(want) + 10))
+    assert worst <= 1e-10, worst
+    perm = rng.permutation(6250)[:512]
+    sub = ps.Data([data.subjects[r] for r in (0, 4999, 9999)])
+    assert np.array_equal(ps.log_likelihood_matrix(eq, sub, spp[perm], ems), psi[[0, 4999, 9999]][:, perm])
+
+
+def test_c4_full_size_properties(ps, oracle, H, W):
+    """C4 at BASELINE size (2,000 x 10,000, RODAS4 at the bench tolerance): finite, spot-checked against a tight
+    explicit-RK oracle run, bit-exact under column permutation (which also changes the work-balanced order)."""
+    w = W.make("c4")
+    eq, data, ems = H.product_objects(w)
+    eq.with_solver(ps.OdeSolver.Rodas4).with_tolerances(1e-6, 1e-6)
+    spp = w["support_points"]
+    psi = ps.log_likelihood_matrix(eq, data, spp, ems)
+    assert psi.shape == (2000, 10000) and np.all(np.isfinite(psi))
+    om, od, oe = H.oracle_objects(w, solver="dopri5", rtol=1e-10, atol=1e-10)
+    rng = np.random.default_rng(13)
+    worst = 0.0
+    for i, j in zip(rng.integers(0, 2000, 150), rng.integers(0, 10000, 150)):
+        want = om.log_likelihood(od.subjects[i], spp[j], oe)
+        worst = max(worst, abs(psi[i, j] - want) / (abs(want) + 8))
+    assert worst <= 2e-4, worst     # rtol = atol = 1e-6 solver; the likelihood amplifies prediction error by |z| pred/sigma
+    perm = rng.permutation(10000)[:2048]
+    assert np.array_equal(ps.log_likelihood_matrix(eq, data, spp[perm], ems), psi[:, perm])
+
+
+def test_c5_reference_stepper_properties(ps, H, W):
+    """C5 (reference adaptive EM + particle filter, 1,000 particles) on a slice of the BASELINE population: the result
+    of a pair depends only on (seed, pair index within the call, parameters), so re-running is bit-identical and
+    -inf (not NaN) marks pairs whose particle likelihood underflows (sde/mod.rs:699-703)."""
+    w = W.make("c5", nsub=8, nspp=64, particles=1000)
+    eq, data, ems = H.product_objects(w)
+    eq.with_particles(1000).with_mode(ps.SdeMode.ParticleFilter).with_seed(42)
+    a = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    b = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    assert np.array_equal(a, b, equal_nan=True) and not np.any(np.isnan(a)) and not np.any(np.isposinf(a))
+    assert np.isfinite(a).mean() > 0.2
