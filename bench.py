@@ -254,6 +254,8 @@ def run_product(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: the image exports NCCL_DEBUG=VERSION, which prints a banner to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("PHARMSOL_B200_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

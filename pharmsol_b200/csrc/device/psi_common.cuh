@@ -52,7 +52,7 @@ template <int N> struct AtLeast1 { static constexpr int v = N > 0 ? N : 1; };
 // Per-pair context shared by the model callbacks.
 template <class M>
 struct PairCtx {
-    double p[AtLeast1<M::NP>::v];
+    double p[AtLeast1<M::NPX>::v];     // parameters, then the pair-invariant slots written by M::prologue
     double cov[AtLeast1<M::NCOV>::v];
     double d[AtLeast1<M::NDER>::v];
     double rate[AtLeast1<M::NROUTE>::v];

@@ -257,6 +257,7 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         PairCtx<M> c;
 #pragma unroll
         for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + q);
+        M::prologue(c.p);
         int status = ST_OK;
         double ll = run_pair<M, SOLVER>(pop, opt, (int)q, c, status, cnt, nullptr, 0);
         if (status != ST_OK) ll = -psi_inf();
@@ -268,6 +269,7 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         PairCtx<M> c;
 #pragma unroll
         for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
+        M::prologue(c.p);
         int status = ST_OK;
         double* pred = (opt.want_pred && out.pred) ? out.pred + j : nullptr;
         const unsigned int work0 = cnt.steps + cnt.rejected;

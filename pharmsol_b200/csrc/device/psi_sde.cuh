@@ -281,6 +281,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
             c.pop = &pop;
 #pragma unroll
             for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
+            M::prologue(c.p);
             Philox ph{(unsigned int)(opt.seed & 0xffffffffull) ^ (unsigned int)(pair >> 32), (unsigned int)(opt.seed >> 32)};
             NormalStream rng; rng.ph = ph;
             int status = ST_OK;

@@ -98,6 +98,53 @@ struct Emitter {
     Ctx& c;
     explicit Emitter(Ctx& cc) : c(cc) {}
 
+    // ---- pair-invariant hoisting ---------------------------------------------------------------------
+    // A sub-expression that reads only parameters and constants has one value per (subject, support
+    // point) pair.  If it contains a division, a power or a function call it is evaluated ONCE per pair in
+    // `prologue` into an extra slot p[NP + k] instead of in every right-hand-side / output evaluation, and a
+    // division by such an expression becomes a multiplication by its hoisted reciprocal (FP64 division is
+    // ~20 instructions on the pipe that bounds these kernels).  The hoisted value is bit-identical to the
+    // in-place one; only the reciprocal rewrite changes results, by at most 1 ulp per division.
+    std::vector<std::string> slots;               // code of slot k (may reference earlier slots)
+    static constexpr int kMaxSlots = 12;
+    int np() const { return (int)c.param_ix.size(); }
+    bool pair_invariant(const ExprP& e, const Scope& s) const {
+        switch (e->kind) {
+            case Expr::Num: case Expr::BoolLit: return true;
+            case Expr::Name: {
+                const std::string& n = e->name;
+                if (s.loop_vars.count(n)) return true;
+                if (s.locals.count(n)) return false;
+                if (n == "t" || n == "time") return false;
+                return c.param_ix.count(n) || c.const_ix.count(n);
+            }
+            case Expr::Index: return false;
+            case Expr::Call: if (e->name == "rate") return false; [[fallthrough]];
+            default:
+                for (const auto& a : e->args) if (!pair_invariant(a, s)) return false;
+                return true;
+        }
+    }
+    static bool expensive(const ExprP& e) {
+        if (e->kind == Expr::Call) return true;
+        if (e->kind == Expr::Binary && (e->name == "/" || e->name == "^")) return true;
+        for (const auto& a : e->args) if (expensive(a)) return true;
+        return false;
+    }
+    // slot holding `code` (deduplicated); "" when the slot budget is exhausted
+    std::string slot_for(const std::string& code) {
+        for (size_t k = 0; k < slots.size(); ++k) if (slots[k] == code) return "p[" + std::to_string(np() + (int)k) + "]";
+        if ((int)slots.size() >= kMaxSlots) return "";
+        slots.push_back(code);
+        return "p[" + std::to_string(np() + (int)slots.size() - 1) + "]";
+    }
+    // code of 1 / y when y is pair-invariant (constant folded, or a hoisted reciprocal); "" otherwise
+    std::string reciprocal(const ExprP& ey, const Val& y, const Scope& s) {
+        if (y.is_const) return (y.cval != 0.0) ? fmt_real(1.0 / y.cval) : "";
+        if (!pair_invariant(ey, s)) return "";
+        return slot_for("(1.0 / " + y.code + ")");
+    }
+
     static Val real(const Val& v) {
         if (v.ty == Ty::Real) return v;
         Val r; r.ty = Ty::Real; r.is_const = v.is_const; r.cval = v.cval;
@@ -153,6 +200,16 @@ struct Emitter {
     }
 
     Val expr(const ExprP& e, Scope& s) {
+        if ((e->kind == Expr::Binary || e->kind == Expr::Call || e->kind == Expr::Unary || e->kind == Expr::IfElse) && expensive(e) && pair_invariant(e, s)) {
+            Val v = expr_raw(e, s);
+            if (v.is_const || v.ty != Ty::Real) return v;
+            const std::string sl = slot_for(v.code);
+            if (sl.empty()) return v;
+            Val r; r.code = sl; return r;
+        }
+        return expr_raw(e, s);
+    }
+    Val expr_raw(const ExprP& e, Scope& s) {
         switch (e->kind) {
             case Expr::Num: {
                 // a literal with zero fractional part is an Int constant even if written 70.0 (analyze.rs:2751-2763)
@@ -223,7 +280,8 @@ struct Emitter {
         if (op == "/") {
             Val x = real(a), y = real(b);
             if (x.is_const && y.is_const) return mkconst(x.cval / y.cval, Ty::Real);
-            Val r; r.code = "(" + x.code + " / " + y.code + ")"; return r;
+            const std::string rc = reciprocal(e->args[1], y, s);
+            Val r; r.code = rc.empty() ? "(" + x.code + " / " + y.code + ")" : "(" + x.code + " * " + rc + ")"; return r;
         }
         if (op == "^") {
             Val x = real(a), y = real(b);
@@ -325,7 +383,8 @@ struct Emitter {
                 }
                 if (op == "/") {
                     // (a/b)' = a'/b - a b'/b^2
-                    std::string t1 = da.empty() ? "" : "(" + da + " / " + b.code + ")";
+                    const std::string rc = reciprocal(e->args[1], b, s);
+                    std::string t1 = da.empty() ? "" : rc.empty() ? "(" + da + " / " + b.code + ")" : "(" + da + " * " + rc + ")";
                     std::string t2 = db.empty() ? "" : "((" + a.code + " * " + db + ") / (" + b.code + " * " + b.code + "))";
                     return t2.empty() ? t1 : t1.empty() ? "(-" + t2 + ")" : "(" + t1 + " - " + t2 + ")";
                 }
@@ -741,12 +800,17 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     H << "    static constexpr int KIND = " << (int)ast.kind << ";\n";
     H << "    static constexpr int NP = " << cm.parameters.size() << ", NCOV = " << cm.covariates.size() << ", NSTATE = " << cm.state_len
       << ", NROUTE = " << cm.route_len << ", NDER = " << cm.derived_len << ", NOUT = " << cm.output_len << ";\n";
+    H << "    static constexpr int NPX = " << (cm.parameters.size() + em.slots.size()) << ";   // parameters + pair-invariant slots filled by prologue()\n";
     H << "    static constexpr int AKERNEL = " << cm.analytical_kernel << ";\n";
     H << "    static constexpr int DERIVE_DEPS = " << derive_deps << ";   // 1 t | 2 covariates | 4 states | 8 rates\n";
     H << "    static constexpr bool HAS_DERIVE = " << (cm.has_derive ? "true" : "false") << ", HAS_INIT = " << (cm.has_init ? "true" : "false")
       << ", HAS_LAG = " << (cm.has_lag ? "true" : "false") << ", HAS_FA = " << (cm.has_fa ? "true" : "false") << ";\n";
     H << "    static constexpr bool RHS_USES_COV = " << (rhs_uses_cov ? "true" : "false") << ", RHS_USES_DERIVED = " << (dyn_reads_derived ? "true" : "false")
       << ", KP_USES_DERIVED = " << (kp_uses_derived ? "true" : "false") << ", RHS_TIME_DEP = " << (rhs_time_dep ? "true" : "false") << ";\n";
+    // pair-invariant slots: evaluated once per (subject, support point) pair right after the parameter load
+    S << "    PSI_DEV static void prologue(double* p) {\n";
+    for (size_t k = 0; k < em.slots.size(); ++k) S << "        p[" << (cm.parameters.size() + k) << "] = " << em.slots[k] << ";\n";
+    S << "    }\n";
     cm.struct_body = H.str() + S.str();
     cm.id = fnv1a_hex(cm.struct_body);
     return cm;
