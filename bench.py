@@ -256,7 +256,18 @@ def run_product(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # keep stdout to the one JSON line: the image exports NCCL_DEBUG=VERSION, which prints a banner to stdout
         os.environ["NCCL_DEBUG"] = os.environ.get("PHARMSOL_B200_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)                      # anything NCCL prints while the communicator comes up goes to stderr
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         torch.cuda.synchronize(dev)

@@ -277,7 +277,7 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         if (out.col_work) atomicAdd(out.col_work + j, cnt.steps + cnt.rejected - work0);
         if (status != ST_OK) {
             ll = psi_nan();
-            report_error(out, (long long)subj + j * (long long)pop.nsub, status);
+            report_error(out, (long long)subj + (j + out.col_base) * (long long)pop.nsub, status);
         }
         if (out.ll) out.ll[(long long)subj + j * out.ld_ll] = ll;
     }

@@ -274,9 +274,12 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
         int* anc = reinterpret_cast<int*>(ws + 2ll * NS * np + np);
         Counters cnt;
         const long long npairs = (long long)pop.nsub * ncols;
-        for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            const int subj = (int)(pair % pop.nsub);
-            const long long j = pair / pop.nsub;
+        for (long long lpair = blockIdx.x; lpair < npairs; lpair += gridDim.x) {
+            const int subj = (int)(lpair % pop.nsub);
+            const long long j = lpair / pop.nsub;
+            // the random streams are keyed by the GLOBAL pair index, so psi does not depend on how the columns are
+            // sharded over GPUs or chunked by the host call
+            const long long pair = (long long)subj + (j + out.col_base) * (long long)pop.nsub;
             PairCtx<M> c;
             c.pop = &pop;
 #pragma unroll

@@ -153,6 +153,7 @@ struct OutView {
     int64_t scratch_stride;
     const int32_t* col_perm;           // optional: thread slot q evaluates column col_perm[q] (work-balanced warps)
     unsigned int* col_work;            // optional (probe launch): per-column solver attempts, atomically accumulated
+    int64_t col_base;                  // global index of local column 0 (column shards / pipelined chunks): error pair = i + (j + col_base) * nsub
 };
 
 }  // namespace psi

@@ -97,6 +97,8 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
         c->c.device = device;
         c->c.sm_count = prop.multiProcessorCount;
         cuda_check(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        cuda_check(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (auto& e : c->c.chunk_ev) cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
         cuda_check(cudaEventCreate(&c->c.ev0), "cudaEventCreate");
         cuda_check(cudaEventCreate(&c->c.ev1), "cudaEventCreate");
         c->c.err_ctr.reserve(5 * sizeof(unsigned long long));
@@ -379,10 +381,24 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
         launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
         c.launches += 1;
-        launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, c.out.as<double>(), nsub, nullptr, 0, 0, c.stream);
-        if (exponentiate) { launch_exp_inplace(c.out.as<double>(), nsub * nspp, c.stream); c.launches += 1; }
-        cuda_check(cudaMemcpyAsync(out, c.out.p, (size_t)nsub * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H psi");
+        // Pipeline over column chunks: psi is column-major, so a block of columns is one contiguous slab; chunk k is
+        // copied device -> host on the copy stream while chunk k+1 is computed.  Chunks of >= 32 MB, at most 8.
+        const int64_t bytes = nsub * nspp * 8;
+        int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(8, bytes / (32ll << 20)));
+        if (nspp < nchunk * 1024) nchunk = 1;
+        const int64_t per = (nspp + nchunk - 1) / nchunk;
+        for (int k = 0; k < nchunk; ++k) {
+            const int64_t c0 = k * per, c1 = std::min<int64_t>(nspp, c0 + per);
+            if (c1 <= c0) break;
+            double* slab = c.out.as<double>() + c0 * nsub;
+            launch_psi(c, m->m, pop->p, c.spp_soa.as<double>() + c0, c1 - c0, nspp, slab, nsub, nullptr, 0, c0, c.stream, nullptr, k == 0);
+            if (exponentiate) { launch_exp_inplace(slab, nsub * (c1 - c0), c.stream); c.launches += 1; }
+            cuda_check(cudaEventRecord(c.chunk_ev[k], c.stream), "chunk event");
+            cuda_check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[k], 0), "chunk wait");
+            cuda_check(cudaMemcpyAsync(out + c0 * nsub, slab, (size_t)(nsub * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "D2H psi");
+        }
         cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+        cuda_check(cudaStreamSynchronize(c.copy_stream), "synchronize");
         return collect(c, code, pair);
     });
 }

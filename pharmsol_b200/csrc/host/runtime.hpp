@@ -40,7 +40,8 @@ struct KernelRef {
 struct Ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
@@ -84,7 +85,7 @@ int effective_solver(const Model& m);
 // --- launches -------------------------------------------------------------------------------------------
 void launch_psi(Ctx& ctx, Model& m, Population& pop, const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                 double* out_dev, int64_t ld_out, double* pred_dev, int64_t ld_pred, int64_t first_col, cudaStream_t stream,
-                const psi::RunOpts* opts_override = nullptr);
+                const psi::RunOpts* opts_override = nullptr, bool reset_status = true);
 void launch_transpose(const double* rows, double* soa, int64_t nspp, int nparams, int64_t ld, cudaStream_t stream);
 void launch_exp_inplace(double* p, int64_t n, cudaStream_t stream);
 double measure_fp64_peak(Ctx& ctx, double* clock_mhz);

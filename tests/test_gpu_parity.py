@@ -636,3 +636,26 @@ def test_c5_reference_stepper_properties(ps, H, W):
     b = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
     assert np.array_equal(a, b, equal_nan=True) and not np.any(np.isnan(a)) and not np.any(np.isposinf(a))
     assert np.isfinite(a).mean() > 0.2
+
+
+def test_host_call_pipelines_chunks_without_changing_psi(ps, H, W):
+    """The host-buffer call splits large outputs into column chunks (compute chunk k+1 while chunk k is copied back).
+    Result must equal the single-launch device-resident path bit for bit, including the first-error pair index."""
+    import torch
+    w = W.make("c1", nsub=3000, nspp=6000)           # 144 MB of psi -> 4 chunks
+    eq, data, ems = H.product_objects(w)
+    host = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    job = ps.ResidentPsi(eq, data, w["support_points"], ems, shard=False)
+    job.launch()
+    resident = job.finish().cpu().numpy()
+    assert np.array_equal(host, resident)
+    # an error in a late chunk still reports its GLOBAL pair index
+    eq2 = ps.Equation.from_dsl(FX.kernel_dsl("two_compartments"))
+    ops = [("bolus", 0.0, 100.0, "0")] + [("observation", float(t), 50.0, "0") for t in range(1, 4)]
+    data2 = ps.Data([ps.Subject(f"s{i}", ops) for i in range(2000)])
+    spp = np.tile(np.array([[0.1, 3.0, 1.0, 1.0]]), (9000, 1))
+    spp[8123] = [1.0, -3.0, 1.5, 1.0]                  # imaginary roots
+    em = ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0))
+    with pytest.raises(ps.PharmsolError) as e:
+        ps.log_likelihood_matrix(eq2, data2, spp, em)
+    assert e.value.code == 12 and e.value.pair == 0 + 8123 * 2000
