@@ -659,3 +659,59 @@ def test_host_call_pipelines_chunks_without_changing_psi(ps, H, W):
     with pytest.raises(ps.PharmsolError) as e:
         ps.log_likelihood_matrix(eq2, data2, spp, em)
     assert e.value.code == 12 and e.value.pair == 0 + 8123 * 2000
+
+
+# ---- reference tests with LITERAL expected values for the DSL path ----------------------------------------------------
+def test_dsl_numeric_equality_literals(ps):
+    """tests/dsl_numeric_equality.rs:13-81: real-valued covariate equality selects branches; exact expected outputs."""
+    src = """
+name = numeric_equality
+kind = ode
+
+params = a, b, c
+covariates = drug
+states = central
+outputs = e, non_integral, not_one
+
+dx(central) = 0
+
+out(e) = if (drug == 1) a else if (drug == 2) b else c
+out(non_integral) = if (drug == 1.1) a else if (drug == 2.1) b else c
+out(not_one) = if (drug != 1) a else b
+"""
+    eq = ps.Equation.from_dsl(src)
+
+    def value(drug, output):
+        ops = [("covariate", "drug", 0.0, drug), ("missing_observation", 0.0, output)]
+        return gpu_predictions(ps, eq, ops, [10.0, 20.0, 30.0])[0]
+    for drug, want in [(1.0, 10.0), (2.0, 20.0), (3.0, 30.0)]:
+        assert value(drug, "e") == want
+    for drug, want in [(1.0, 30.0), (2.0, 30.0), (3.0, 30.0), (1.1, 10.0), (2.1, 20.0), (3.1, 30.0)]:
+        assert value(drug, "non_integral") == want
+    for drug, want in [(1.0, 20.0), (2.0, 10.0), (3.0, 10.0), (1.1, 10.0), (2.1, 10.0), (3.1, 10.0)]:
+        assert value(drug, "not_one") == want
+
+
+@pytest.mark.parametrize("keyword", ["t", "time"])
+def test_dsl_time_keyword(ps, keyword):
+    """tests/dsl_time_keyword.rs:10-80: `t` / `time` is the current simulation time in outputs."""
+    src = f"""
+name = time_probe
+kind = ode
+
+params = ke
+states = central
+outputs = cp, time_echo
+
+infusion(iv) -> central
+
+dx(central) = -ke * central
+
+out(cp) = central
+out(time_echo) = {keyword}
+"""
+    eq = ps.Equation.from_dsl(src)
+    times = [0.5, 1.0, 2.5, 4.0]
+    ops = [("infusion", 0.0, 100.0, "iv", 1.0)] + [("missing_observation", t, "time_echo") for t in times]
+    got = gpu_predictions(ps, eq, ops, [1.0])
+    assert len(got) == 4 and np.max(np.abs(got - np.array(times))) < 1e-6
