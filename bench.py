@@ -82,6 +82,8 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused all-gather by peer stores from the psi kernel (default) or a separate NCCL all-gather")
     return ap.parse_args()
 
 
@@ -151,7 +153,7 @@ def make_workload(args, world):
 
 def config_dict(args, w, nsub, nspp_per_gpu, world):
     cfg = {"workload": f"{args.workload}: {w['desc']}", "nsub": nsub, "nspp_per_gpu": nspp_per_gpu, "nspp_total": nspp_per_gpu * world,
-           "sharding": f"support-point columns x{world}" + (" + NCCL all-gather of psi slabs" if world > 1 else ""),
+           "sharding": f"support-point columns x{world}",
            "l2": "512 MiB device memset between timed iterations (outside the event bracket)"}
     if w["kind"] == "ode":
         cfg.update(solver=WORKLOADS[args.workload]["solver"], rtol=args.tol, atol=args.tol)
@@ -296,7 +298,8 @@ def run_product(args):
         eq.with_solver(getattr(ps.OdeSolver, cfg["solver"])).with_tolerances(args.tol, args.tol)
     if w["kind"] == "sde":
         eq.with_particles(args.particles).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.ReferenceAdaptive)
-    job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev)
+    job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=(args.gather == "peer"))
+    fused = getattr(job.sharded, "peer_ptrs", None) is not None
     ctx = job.ctx
     npairs_rank = nsub * job.ncols
     npairs_total = nsub * nspp_per_gpu * world
@@ -394,7 +397,9 @@ def run_product(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config_dict(args, w, nsub, nspp_per_gpu, world),
+                "data": "synthetic", "config": dict(config_dict(args, w, nsub, nspp_per_gpu, world),
+                                                    gather=("none (1 GPU)" if world == 1 else "fused: psi kernel stores to every rank over NVLink + device barrier"
+                                                            if fused else "NCCL all_gather_into_tensor (in place)")),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "psi_nan": n_nan, "psi_neg_inf": n_neginf, "wall_s_timed_region": t_wall, "fp64_peak_clock_mhz": clk}
         print(json.dumps(line), flush=True)

@@ -204,6 +204,16 @@ int32_t pharmsol_cuda_log_likelihood_matrix(pcu_ctx* ctx, pcu_model* m, pcu_popu
 int32_t pharmsol_cuda_log_likelihood_matrix_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
                                                    const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                                                    double* out_dev, int64_t ld_out, int64_t first_col, void* stream);
+/* Column-sharded psi with the all-gather FUSED into the kernel: every result is stored directly into the full
+ * column-major psi of every rank through peer-mapped pointers (NVLink / NVSwitch), at global column
+ * first_col + j, so no separate collective copies slabs afterwards.
+ *   out_full_peers   host array of npeers (<= 8) DEVICE pointers, one full (ld_out x nspp_total) matrix per rank,
+ *                    each dereferenceable from this device (CUDA IPC / symmetric memory / cudaDeviceEnablePeerAccess)
+ * The caller synchronises the ranks (a device barrier) before any rank reads its matrix. */
+int32_t pharmsol_cuda_log_likelihood_matrix_peers(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                                  const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                                                  double* const* out_full_peers, int32_t npeers, int64_t ld_out,
+                                                  int64_t first_col, void* stream);
 int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* first_error_code, int64_t* first_error_pair);
 /* row-major host support points -> SoA device buffer (H2D + on-device transpose) */
 int32_t pharmsol_cuda_upload_support_points(pcu_ctx* ctx, const double* support_points, int64_t nspp, int32_t nparams,

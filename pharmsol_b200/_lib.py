@@ -121,6 +121,7 @@ def lib():
         "pharmsol_cuda_population_device_bytes": (i64, [vp]),
         "pharmsol_cuda_log_likelihood_matrix": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
         "pharmsol_cuda_log_likelihood_matrix_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, i64, vp]),
+        "pharmsol_cuda_log_likelihood_matrix_peers": (i32, [vp, vp, vp, vp, i64, i64, P(vp), i32, i64, i64, vp]),
         "pharmsol_cuda_collect_errors": (i32, [vp, P(i32), P(i64)]),
         "pharmsol_cuda_upload_support_points": (i32, [vp, dp, i64, i32, vp, i64, vp]),
         "pharmsol_cuda_predictions": (i32, [vp, vp, vp, dp, i64, i32, dp]),
@@ -462,3 +463,10 @@ def log_likelihood_batch(ctx, model, pop, parameters, residual_models):
     out = np.empty(pop.nsubjects, dtype=np.float64)
     check(lib().pharmsol_cuda_log_likelihood_batch(ctx.ptr, model.ptr, pop.ptr, _dp(prm), prm.shape[0], prm.shape[1], arr, n, _dp(out)))
     return out
+
+
+def log_likelihood_matrix_peers(ctx, model, pop, spp_soa_ptr, ncols, ld_spp, peer_ptrs, ld_out, first_col, stream=0):
+    """Asynchronous launch that stores every result into the full psi of every rank (fused all-gather)."""
+    arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(q)) for q in peer_ptrs])
+    check(lib().pharmsol_cuda_log_likelihood_matrix_peers(ctx.ptr, model.ptr, pop.ptr, C.c_void_p(int(spp_soa_ptr)), int(ncols), int(ld_spp),
+                                                          arr, len(peer_ptrs), int(ld_out), int(first_col), C.c_void_p(int(stream) or None)))

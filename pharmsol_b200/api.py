@@ -610,7 +610,8 @@ class ResidentPsi:
     torch is used for device memory, streams and the process group only.
     """
 
-    def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True):
+    def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True,
+                 peer_stores=True):
         import torch
         import torch.distributed as dist
         from .sharding import ShardedPsi
@@ -625,7 +626,7 @@ class ResidentPsi:
         spp = np.ascontiguousarray(support_points, dtype=np.float64)
         self.nspp, self.nparams = spp.shape
         self.nsub = self.pop.nsubjects
-        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device) if (shard and dist.is_available() and dist.is_initialized()) \
+        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=peer_stores) if (shard and dist.is_available() and dist.is_initialized()) \
             else _SingleRank(self.nsub, self.nspp, self.device)
         lo, hi = self.sharded.local_range
         self.first_col, self.ncols = lo, hi - lo
@@ -645,6 +646,11 @@ class ResidentPsi:
     def launch(self):
         """One asynchronous psi kernel launch for this rank's columns (no copies, no sync)."""
         if not self.ncols:
+            return
+        peers = getattr(self.sharded, "peer_ptrs", None)
+        if peers is not None:      # fused all-gather: results go straight into every rank's full matrix
+            _lib.log_likelihood_matrix_peers(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,
+                                             peers, self.nsub, self.first_col, self._stream())
             return
         slab = self.sharded.local_slab()
         _lib.log_likelihood_matrix_device(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,

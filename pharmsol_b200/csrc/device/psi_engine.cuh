@@ -279,7 +279,14 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
             ll = psi_nan();
             report_error(out, (long long)subj + (j + out.col_base) * (long long)pop.nsub, status);
         }
-        if (out.ll) out.ll[(long long)subj + j * out.ld_ll] = ll;
+        if (out.npeers > 0) {
+            const long long at = (long long)subj + (j + out.col_base) * out.ld_ll;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < out.npeers) out.ll_peers[r][at] = ll;      // posted 8-byte stores, one per rank
+        } else if (out.ll) {
+            out.ll[(long long)subj + j * out.ld_ll] = ll;
+        }
     }
     flush_counters(out, cnt);
 }

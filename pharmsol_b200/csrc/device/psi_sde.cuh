@@ -460,7 +460,12 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
             }
             if (tid == 0) {
                 if (status != ST_OK) { ll = psi_nan(); report_error(out, pair, status); }
-                if (out.ll) out.ll[(long long)subj + j * out.ld_ll] = ll;
+                if (out.npeers > 0) {
+                    const long long at = (long long)subj + (j + out.col_base) * out.ld_ll;
+                    for (int r = 0; r < out.npeers; ++r) out.ll_peers[r][at] = ll;
+                } else if (out.ll) {
+                    out.ll[(long long)subj + j * out.ld_ll] = ll;
+                }
             }
             __syncthreads();
             flush_counters(out, cnt);      // per pair: the 32-bit per-thread counters would wrap over a long grid-stride loop

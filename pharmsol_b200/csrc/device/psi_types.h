@@ -153,6 +153,12 @@ struct OutView {
     int64_t scratch_stride;
     const int32_t* col_perm;           // optional: thread slot q evaluates column col_perm[q] (work-balanced warps)
     unsigned int* col_work;            // optional (probe launch): per-column solver attempts, atomically accumulated
+    // Fused all-gather: when npeers > 0 every result is stored straight into the FULL column-major psi of every rank
+    // (peer pointers mapped over NVLink / NVSwitch) at its global column, instead of into a local slab that a
+    // separate collective copies afterwards.  ll is ignored then.
+    double* ll_peers[8];
+    int32_t npeers;
+    int32_t pad_;
     int64_t col_base;                  // global index of local column 0 (column shards / pipelined chunks): error pair = i + (j + col_base) * nsub
 };
 

@@ -341,6 +341,19 @@ int32_t pharmsol_cuda_log_likelihood_matrix_device(pcu_ctx* ctx, pcu_model* m, p
         return (int32_t)PCU_OK;
     });
 }
+int32_t pharmsol_cuda_log_likelihood_matrix_peers(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev, int64_t ncols,
+                                                  int64_t ld_spp, double* const* out_full_peers, int32_t npeers, int64_t ld_out,
+                                                  int64_t first_col, void* stream) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp_soa_dev || !out_full_peers || npeers < 1 || npeers > 8 || ld_out < pop->p.flat.nsub) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        for (int r = 0; r < npeers; ++r) if (!out_full_peers[r]) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        launch_psi(ctx->c, m->m, pop->p, spp_soa_dev, ncols, ld_spp, nullptr, ld_out, nullptr, 0, first_col, pick_stream(ctx->c, stream), nullptr, true,
+                   out_full_peers, npeers);
+        return (int32_t)PCU_OK;
+    });
+}
 int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev, int64_t ncols,
                                          int64_t ld_spp, double* pred_dev, int64_t ld_pred, double* ll_dev, int64_t ld_out, void* stream) {
     return guarded([&] {

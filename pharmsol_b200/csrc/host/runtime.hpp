@@ -85,7 +85,7 @@ int effective_solver(const Model& m);
 // --- launches -------------------------------------------------------------------------------------------
 void launch_psi(Ctx& ctx, Model& m, Population& pop, const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                 double* out_dev, int64_t ld_out, double* pred_dev, int64_t ld_pred, int64_t first_col, cudaStream_t stream,
-                const psi::RunOpts* opts_override = nullptr, bool reset_status = true);
+                const psi::RunOpts* opts_override = nullptr, bool reset_status = true, double* const* peers = nullptr, int npeers = 0);
 void launch_transpose(const double* rows, double* soa, int64_t nspp, int nparams, int64_t ld, cudaStream_t stream);
 void launch_exp_inplace(double* p, int64_t n, cudaStream_t stream);
 double measure_fp64_peak(Ctx& ctx, double* clock_mhz);

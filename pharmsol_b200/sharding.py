@@ -60,7 +60,7 @@ class ShardedPsi:
     and return ``(error_code, first_failing_global_pair)``.
     """
 
-    def __init__(self, nsub: int, nspp: int, device, dtype=None, group=None):
+    def __init__(self, nsub: int, nspp: int, device, dtype=None, group=None, peer_stores=False):
         import torch
         import torch.distributed as dist
         self.dist = dist
@@ -71,7 +71,22 @@ class ShardedPsi:
         self.nsub, self.nspp = int(nsub), int(nspp)
         self.device = device
         # column-major psi == C-order (columns, nsub); padded to world * shard columns
-        self.full = torch.empty((self.part.padded, self.nsub), dtype=dtype or torch.float64, device=device)
+        # Fused all-gather: allocate psi in symmetric memory so every rank's full matrix is mapped into every
+        # process (NVLink / NVSwitch peer pointers); the psi kernel then stores each result to all ranks directly
+        # and `gather` degenerates to a device barrier.  Falls back to the NCCL all-gather if the rendezvous fails.
+        self.symm, self.peer_ptrs = None, None
+        self.full = None
+        if peer_stores and self.world > 1 and torch.device(device).type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.full = symm_mem.empty((self.part.padded, self.nsub), dtype=dtype or torch.float64, device=device)
+                self.symm = symm_mem.rendezvous(self.full, group if group is not None else dist.group.WORLD)
+                self.peer_ptrs = [int(q) for q in self.symm.buffer_ptrs]
+            except Exception as e:      # noqa: BLE001 - any failure means "no peer mapping available"
+                self.symm, self.peer_ptrs, self.full = None, None, None
+                self.peer_error = repr(e)
+        if self.full is None:
+            self.full = torch.empty((self.part.padded, self.nsub), dtype=dtype or torch.float64, device=device)
         self._err = torch.zeros(1, dtype=torch.int64, device=device)
 
     @property
@@ -84,9 +99,13 @@ class ShardedPsi:
         return self.full[self.rank * s:(self.rank + 1) * s]
 
     def gather(self):
-        """In-place all-gather of the slabs (each rank's input IS its slice of the output)."""
+        """In-place all-gather of the slabs (each rank's input IS its slice of the output); with peer stores the
+        kernel has already written every rank's matrix and only a device barrier over the ranks remains."""
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.full, self.local_slab(), group=self.group)
+            if self.peer_ptrs is not None:
+                self.symm.barrier()
+            else:
+                self.dist.all_gather_into_tensor(self.full, self.local_slab(), group=self.group)
         return self.full
 
     def reduce_error(self, code: int, pair: int):
