@@ -715,3 +715,30 @@ out(time_echo) = {keyword}
     ops = [("infusion", 0.0, 100.0, "iv", 1.0)] + [("missing_observation", t, "time_echo") for t in times]
     got = gpu_predictions(ps, eq, ops, [1.0])
     assert len(got) == 4 and np.max(np.abs(got - np.array(times))) < 1e-6
+
+
+def test_concurrent_host_threads_share_one_equation(ps, H, W):
+    """`Equation: Sync` (equation/mod.rs:377): one model / population / context used from several host threads at once
+    (ctypes releases the GIL, the library serialises per context) gives the serial results."""
+    import threading
+    w = W.make("c2", nsub=24, nspp=512)
+    eq, data, ems = H.product_objects(w)
+    eq.with_solver(ps.OdeSolver.Dopri5).with_tolerances(1e-6, 1e-6)
+    spp = w["support_points"]
+    serial = [ps.log_likelihood_matrix(eq, data, spp[k * 128:(k + 1) * 128], ems) for k in range(4)]
+    out, errs = [None] * 4, []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                out[k] = ps.log_likelihood_matrix(eq, data, spp[k * 128:(k + 1) * 128], ems)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        assert np.array_equal(out[k], serial[k])
