@@ -82,8 +82,9 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: fused all-gather by peer stores from the psi kernel (default) or a separate NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: fused all-gather by peer stores from the psi kernel, a separate NCCL all-gather, or auto "
+                         "(fused for ODE / SDE models, NCCL for closed-form models whose psi is produced at GB/s rates)")
     return ap.parse_args()
 
 
@@ -298,7 +299,7 @@ def run_product(args):
         eq.with_solver(getattr(ps.OdeSolver, cfg["solver"])).with_tolerances(args.tol, args.tol)
     if w["kind"] == "sde":
         eq.with_particles(args.particles).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.ReferenceAdaptive)
-    job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=(args.gather == "peer"))
+    job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=("auto" if args.gather == "auto" else args.gather == "peer"))
     fused = getattr(job.sharded, "peer_ptrs", None) is not None
     ctx = job.ctx
     npairs_rank = nsub * job.ncols

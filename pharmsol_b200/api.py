@@ -611,7 +611,7 @@ class ResidentPsi:
     """
 
     def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True,
-                 peer_stores=True):
+                 peer_stores="auto"):
         import torch
         import torch.distributed as dist
         from .sharding import ShardedPsi
@@ -626,7 +626,12 @@ class ResidentPsi:
         spp = np.ascontiguousarray(support_points, dtype=np.float64)
         self.nspp, self.nparams = spp.shape
         self.nsub = self.pop.nsubjects
-        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=peer_stores) if (shard and dist.is_available() and dist.is_initialized()) \
+        if peer_stores == "auto":
+            # 8-byte peer stores are one NVLink packet each: they win when a pair costs microseconds (ODE / SDE: C2 on
+            # 8 GPUs 42.8 ms fused vs 44.3 ms with NCCL) and lose when psi is produced at GB/s rates (closed forms: C3 on
+            # 8 GPUs 63.5 ms fused vs 57.0 ms with the bulk NCCL all-gather)
+            peer_stores = equation.kind() != EqnKind.Analytical
+        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=bool(peer_stores)) if (shard and dist.is_available() and dist.is_initialized()) \
             else _SingleRank(self.nsub, self.nspp, self.device)
         lo, hi = self.sharded.local_range
         self.first_col, self.ncols = lo, hi - lo
