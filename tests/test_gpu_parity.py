@@ -742,3 +742,40 @@ def test_concurrent_host_threads_share_one_equation(ps, H, W):
     assert not errs, errs
     for k in range(4):
         assert np.array_equal(out[k], serial[k])
+
+
+def test_solver_failure_is_a_status_not_a_hang(ps):
+    """A finite-time blow-up (dx = x^2) cannot be integrated: every solver must give PharmsolError(SolverFailure = 7)
+    for the failing pair (DiffsolError in the reference) and keep the healthy pair finite."""
+    src = "name = blowup\nkind = ode\nparams = k, v\nstates = x\noutputs = cp\nbolus(iv) -> x\ndx(x) = k * x * x\nout(cp) = x / v ~ continuous()\n"
+    ops = [("bolus", 0.0, 1.0, "iv"), ("observation", 0.5, 1.0, "cp"), ("observation", 3.0, 1.0, "cp")]
+    em = ps.AssayErrorModels().add("cp", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0))
+    spp = np.array([[0.1, 1.0], [1.0, 1.0]])        # k = 1 blows up at t = 1
+    for solver in ("Dopri5", "Tsit45", "Rodas4", "Sdirk4", "TrBdf2"):
+        eq = ps.Equation.from_dsl(src).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(1e-6, 1e-6).with_max_steps(20000)
+        with pytest.raises(ps.PharmsolError) as e:
+            ps.log_likelihood_matrix(eq, ps.Data([ps.Subject("a", ops)]), spp, em)
+        assert e.value.code == 7 and e.value.pair == 1, (solver, e.value.code, e.value.pair)
+        ok = ps.log_likelihood_matrix(eq, ps.Data([ps.Subject("a", ops)]), spp[:1], em)
+        assert np.isfinite(ok).all()
+
+
+def test_more_subjects_than_grid_rows(ps, oracle):
+    """nsub > 65535 (the grid's y extent): the CTA loops over subjects."""
+    n = 66000
+    rng = np.random.default_rng(5)
+    amt = rng.uniform(100, 600, n)
+    subs = [(f"s{i}", [("infusion", 0.0, float(amt[i]), "iv", 0.5), ("observation", 1.0, 2.0, "cp"), ("observation", 6.0, 0.7, "cp")]) for i in range(n)]
+    from benches import workloads
+    eq = ps.Equation.from_dsl(workloads.model_source("c1_one_cpt_iv"))
+    data = ps.Data([ps.Subject(i, o) for i, o in subs])
+    em = ("additive", 0.0, (0.1, 0.1, 0.0, 0.0))
+    spp = np.array([[0.3, 100.0], [0.7, 60.0], [0.1, 200.0]])
+    psi = ps.log_likelihood_matrix(eq, data, spp, ps.AssayErrorModels().add("cp", ps.AssayErrorModel.additive(ps.ErrorPoly(*em[2]), 0.0)))
+    assert psi.shape == (n, 3) and np.all(np.isfinite(psi))
+    om = oracle.Model("one_cpt_iv")
+    oe = oracle.ErrorModels([em])
+    for i in (0, 1, 65534, 65535, 65536, n - 1):
+        for j in range(3):
+            want = om.log_likelihood(oracle.Subject(subs[i][1]), spp[j], oe)
+            assert abs(psi[i, j] - want) <= 1e-12 * (abs(want) + 2)
