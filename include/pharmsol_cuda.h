@@ -138,6 +138,9 @@ int64_t pharmsol_data_len(const pcu_data* d);
  * OUT = -99 is a missing observation.  Errors: PCU_ERR_OTHER with the message in last_error_message. */
 int32_t pharmsol_data_read_pmetrics(const char* path, pcu_data** out);
 int32_t pharmsol_data_from_pmetrics_text(const char* text, size_t len, pcu_data** out);
+/* Data::expand (src/data/structs.rs:155-260): a copy with missing observations added every `idelta` from 0 to the
+ * last dose end + `tad` (per occasion, every output label of the dataset) — dense prediction grids. */
+int32_t pharmsol_data_expand(const pcu_data* d, double idelta, double tad, pcu_data** out);
 /* JSON description (subjects -> occasions -> events, covariates) for inspection; returns the number of bytes
  * needed (excluding the terminator) and writes at most cap - 1 bytes + NUL into buf (buf may be NULL). */
 int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap);

@@ -97,6 +97,7 @@ def lib():
         "pharmsol_data_read_pmetrics": (i32, [cs, P(vp)]),
         "pharmsol_data_from_pmetrics_text": (i32, [cs, sz, P(vp)]),
         "pharmsol_data_describe_json": (i64, [vp, C.c_char_p, sz]),
+        "pharmsol_data_expand": (i32, [vp, d, d, P(vp)]),
         "pharmsol_cuda_model_from_dsl": (i32, [vp, cs, sz, P(vp)]),
         "pharmsol_cuda_model_destroy": (None, [vp]),
         "pharmsol_cuda_model_kind": (i32, [vp]),
@@ -275,6 +276,11 @@ class NativeData:
         else:
             check(lib().pharmsol_data_read_pmetrics(_b(path), C.byref(ptr)))
         return cls(ptr=ptr)
+
+    def expand(self, idelta, tad):
+        ptr = C.c_void_p()
+        check(lib().pharmsol_data_expand(self.ptr, float(idelta), float(tad), C.byref(ptr)))
+        return NativeData(ptr=ptr)
 
     def describe(self):
         import json

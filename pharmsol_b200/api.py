@@ -132,7 +132,14 @@ class Data:
     def from_pmetrics(cls, path=None, text=None):
         """read_pmetrics (data/parser/pmetrics/mod.rs:164-239): the CSV is parsed natively (C++), ADDL/II expanded,
         occasions split at EVID=4; ``subjects`` mirrors the parsed result as builder ops."""
-        native = _lib.NativeData.from_pmetrics(path=path, text=text)
+        return cls._from_native(_lib.NativeData.from_pmetrics(path=path, text=text))
+
+    def expand(self, idelta, tad):
+        """Data::expand (data/structs.rs:155-260): dense prediction grid of missing observations."""
+        return Data._from_native(self.native().expand(idelta, tad))
+
+    @classmethod
+    def _from_native(cls, native):
         subjects = []
         cens = {0: Censor.NONE, 1: Censor.BLOQ, 2: Censor.ALOQ}
         for s in native.describe():

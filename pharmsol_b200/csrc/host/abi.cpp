@@ -178,6 +178,15 @@ int32_t pharmsol_data_from_pmetrics_text(const char* text, size_t len, pcu_data*
         return (int32_t)PCU_OK;
     });
 }
+int32_t pharmsol_data_expand(const pcu_data* d, double idelta, double tad, pcu_data** out) {
+    return guarded([&] {
+        if (!d || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        auto* n = new pcu_data();
+        try { n->d = expand_data(d->d, idelta, tad); } catch (...) { delete n; throw; }
+        *out = n;
+        return (int32_t)PCU_OK;
+    });
+}
 int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap) {
     if (!d) return -1;
     const std::string s = describe_data_json(d->d);

@@ -92,6 +92,7 @@ struct Data {
 Data read_pmetrics_text(const std::string& text);
 Data read_pmetrics_file(const std::string& path);
 std::string describe_data_json(const Data& d);
+Data expand_data(const Data& d, double idelta, double tad);      // Data::expand (data/structs.rs:155-260)
 
 enum class ErrKind : int { None = 0, Additive = 1, Proportional = 2 };
 struct AssayErrorModel {

@@ -271,6 +271,49 @@ Data read_pmetrics_file(const std::string& path) {
     return read_pmetrics_text(ss.str());
 }
 
+// Data::expand (data/structs.rs:155-260): add missing observations on a regular grid (every `idelta` from 0 to the
+// last dose end + `tad`, per occasion, for every output label of the dataset) unless an observation of that output
+// already exists at that time (compared in integer microseconds) — dense prediction grids.
+Data expand_data(const Data& d, double idelta, double tad) {
+    if (!(idelta > 0.0)) return d;
+    const unsigned long long step_us = (unsigned long long)std::llround(idelta * 1e6);
+    if (step_us == 0) return d;
+    std::set<std::string> outeqs;                         // sorted + deduplicated (structs.rs:294-304)
+    for (const auto& s : d.subjects) for (const auto& o : s.occasions) for (const auto& e : o.events)
+        if (e.kind == EventKind::Observation) outeqs.insert(e.label);
+    Data out;
+    for (const auto& s : d.subjects) {
+        Subject ns; ns.id = s.id;
+        for (const auto& o : s.occasions) {
+            double last = 0.0; bool any = false;
+            for (const auto& e : o.events) {
+                if (e.kind == EventKind::Observation) continue;
+                const double t = e.kind == EventKind::Bolus ? e.time : e.time + e.duration;
+                if (!any || t > last) { last = t; any = true; }
+            }
+            last = (any ? last : 0.0) + tad;
+            std::set<std::pair<unsigned long long, std::string>> existing;
+            for (const auto& e : o.events)
+                if (e.kind == EventKind::Observation) existing.insert({(unsigned long long)std::llround(e.time * 1e6), e.label});
+            Occasion no; no.index = o.index; no.covariates = o.covariates;
+            const double last_us_f = std::round(last * 1e6);
+            const unsigned long long last_us = last_us_f < 0.0 ? 0ull : (unsigned long long)last_us_f;   // Rust `as u64` saturates at 0
+            for (unsigned long long key = 0; key <= last_us; key += step_us) {
+                for (const auto& lab : outeqs) {
+                    if (existing.count({key, lab})) continue;
+                    Event e; e.kind = EventKind::Observation; e.time = (double)key / 1e6; e.label = lab; e.has_value = false; e.occasion = o.index;
+                    no.events.push_back(e);
+                }
+            }
+            no.events.insert(no.events.end(), o.events.begin(), o.events.end());
+            no.sort();
+            ns.occasions.push_back(std::move(no));
+        }
+        out.subjects.push_back(std::move(ns));
+    }
+    return out;
+}
+
 // JSON description of a dataset (inspection / tests): subjects -> occasions -> events + covariates.
 std::string describe_data_json(const Data& d) {
     std::ostringstream o;

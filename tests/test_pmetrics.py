@@ -133,3 +133,25 @@ def test_parsed_data_feeds_the_oracle_and_the_builder_ops(ps, oracle):
     assert s.n_occasions() == 2
     pr = oracle.Model("one_cpt_iv").predictions(s, [0.3, 100.0])
     assert len(pr) == 3 and np.all(np.isfinite(pr))
+
+
+def _obs_times(occ):
+    return sorted(e["time"] for e in occ["events"] if e["kind"] == "observation")
+
+
+def test_expand_grid_reaches_last_dose_plus_tad(ps):
+    # data/structs.rs:1700-1723
+    d = ps.Data([ps.Subject.builder("s1").bolus(0.0, 100.0, 0).observation(0.0, 5.0, 0).build()]).expand(1.0, 3.0)
+    assert _obs_times(d.native().describe()[0]["occasions"][0]) == [0.0, 1.0, 2.0, 3.0]
+    # the original observation keeps its value, the grid points are missing observations
+    ev = [e for e in d.native().describe()[0]["occasions"][0]["events"] if e["kind"] == "observation"]
+    assert sum(e["value"] is not None for e in ev) == 1
+
+
+def test_expand_last_time_is_per_occasion(ps):
+    # data/structs.rs:1726-1760
+    s = (ps.Subject.builder("s1").bolus(0.0, 100.0, 0).observation(0.0, 5.0, 0).reset()
+         .bolus(10.0, 100.0, 0).observation(10.0, 5.0, 0).build())
+    occ = ps.Data([s]).expand(5.0, 0.0).native().describe()[0]["occasions"]
+    assert _obs_times(occ[0]) == [0.0] and _obs_times(occ[1]) == [0.0, 5.0, 10.0]
+    assert ps.Data([s]).expand(0.0, 5.0).native().describe()[0]["occasions"][0]["events"].__len__() == 2     # idelta <= 0: unchanged
