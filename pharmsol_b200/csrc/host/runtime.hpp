@@ -45,6 +45,7 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
+    unsigned long long* err_host = nullptr;   // pinned mirror of err_ctr, filled by an async copy queued behind the kernels
     DevBuf spp_rows, spp_soa, out, pred, scratch;
     DevBuf col_work, col_idx, col_sort;      // work-balanced column order (ODE): probe counts, permutation, cub scratch
     int64_t launches = 0;
