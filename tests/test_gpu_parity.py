@@ -779,3 +779,58 @@ def test_more_subjects_than_grid_rows(ps, oracle):
         for j in range(3):
             want = om.log_likelihood(oracle.Subject(subs[i][1]), spp[j], oe)
             assert abs(psi[i, j] - want) <= 1e-12 * (abs(want) + 2)
+
+
+def test_particle_filter_converges_to_the_kalman_likelihood(ps, W):
+    """Independent truth for the SDE path: the C5 model is linear-Gaussian (dx = -ke x + rate, additive diffusion sigma,
+    Gaussian assay error), so the exact likelihood is a Kalman filter.  With small fixed EM steps and many particles the
+    particle-filter estimate (log of the seed-averaged likelihood) must converge to it.  Euler-Maruyama and the reference's
+    closed-interval drift-rate rule `start <= t <= start + dur` (one extra step of infusion) are O(dt) biased, so the test
+    checks first-order convergence: the bias at dt = 0.001 is small and ~10x smaller than at dt = 0.01."""
+    amt, dur, v_true = 500.0, 1.0, 100.0
+    t_obs = [0.5, 1.0, 2.0, 3.0, 4.0, 6.0, 8.0, 12.0]
+    rng = np.random.default_rng(21)
+    y = [float(amt / dur / 0.4 * (1 - math.exp(-0.4 * min(t, dur))) * math.exp(-0.4 * max(t - dur, 0.0)) / v_true * math.exp(0.1 * rng.standard_normal())) for t in t_obs]
+    ops = [("infusion", 0.0, amt, "iv", dur)] + [("observation", t, yy, "cp") for t, yy in zip(t_obs, y)]
+    spp = np.array([[0.4, 2.0, 100.0], [0.3, 5.0, 90.0], [0.6, 1.0, 120.0], [0.4, 8.0, 100.0]])      # ke, sigma, v
+    c0, c1 = 0.1, 0.1
+
+    def kalman(ke, sig, v):
+        m, P, t, ll = 0.0, 0.0, 0.0, 0.0
+        for tk, yk in zip(t_obs, y):
+            # propagate across [t, tk], splitting at the infusion end
+            for (a, b) in ([(t, min(tk, dur)), (min(tk, dur), tk)] if t < dur < tk else [(t, tk)]):
+                if b <= a:
+                    continue
+                dt, r = b - a, (amt / dur if b <= dur else 0.0)
+                e = math.exp(-ke * dt)
+                m = m * e + r / ke * (1 - e)
+                P = P * e * e + sig * sig * (1 - e * e) / (2 * ke)
+            t = tk
+            s = c0 + c1 * yk                                  # additive error model: sigma from the observation
+            S = P / (v * v) + s * s
+            innov = yk - m / v
+            ll += -0.5 * math.log(2 * math.pi * S) - 0.5 * innov * innov / S
+            K = (P / v) / S
+            m, P = m + K * innov, P - K * P / v
+        return ll
+    data = ps.Data([ps.Subject("a", ops)])
+    ems = ps.AssayErrorModels().add("cp", ps.AssayErrorModel.additive(ps.ErrorPoly(c0, c1, 0.0, 0.0), 0.0))
+    exact = np.array([kalman(*p) for p in spp])
+    nseed = 16
+
+    def estimate(dt):
+        eq = ps.Equation.from_dsl(W.model_source("c5_one_cpt_sde"))
+        eq.with_particles(8192).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.FixedStep, dt)
+        ll = np.stack([ps.log_likelihood_matrix(eq.with_seed(7000 + s), data, spp, ems)[0] for s in range(nseed)])     # (nseed, 4)
+        shift = ll.max(axis=0)
+        lik = np.exp(ll - shift)
+        return np.log(lik.mean(axis=0)) + shift, lik.std(axis=0, ddof=1) / math.sqrt(nseed) / lik.mean(axis=0)
+    est_c, se_c = estimate(0.01)
+    est_f, se_f = estimate(0.001)
+    err_c, err_f = est_c - exact, est_f - exact
+    # converged: within 0.15 log-units (of |ll| up to 20) at dt = 0.001, Monte-Carlo error negligible
+    assert np.all(np.abs(err_f) <= 0.15 + 4 * se_f), (est_f, exact, se_f)
+    # first order in dt: a 10x smaller step gives a ~10x smaller bias for every support point
+    ratio = err_c / err_f
+    assert np.all((ratio > 6.0) & (ratio < 15.0)), (err_c, err_f, ratio)
