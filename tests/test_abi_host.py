@@ -198,3 +198,21 @@ def test_error_models_bind_by_label(ps):
     with pytest.raises(ps.PharmsolError) as e:
         ps.AssayErrorModels().add("nope", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0)).bound(eq.output_names())
     assert e.value.code == 11
+
+
+def test_macro_style_builders_lower_to_the_same_model_as_dsl_text(ps):
+    """analytical!{..} / ode!{..} / sde!{..} declarations (pharmsol-macros/src/expand/*.rs) mirrored as builders that take
+    DSL expression strings: they must lower to the same compiled model (same id = same generated CUDA) as the text form."""
+    from benches import workloads as W
+    a = ps.analytical(name="one_cpt_iv", params=["ke", "v"], states=["central"], outputs=["cp"], routes=["infusion(iv) -> central"],
+                      structure="one_compartment", out={"cp": "central / v"})
+    assert a._model.id == ps.Equation.from_dsl(W.model_source("c1_one_cpt_iv"))._model.id and a.kind() == ps.EqnKind.Analytical
+    o = ps.ode(name="two_cpt_oral", params=["ka", "ke", "kcp", "kpc", "v"], states=["depot", "central", "peripheral"], outputs=["cp"],
+               routes=["bolus(oral) -> depot"],
+               diffeq={"depot": "-ka * depot", "central": "ka * depot - (ke + kcp) * central + kpc * peripheral",
+                       "peripheral": "kcp * central - kpc * peripheral"}, out={"cp": "central / v"})
+    assert o._model.id == ps.Equation.from_dsl(W.model_source("c2_two_cpt_oral_ode"))._model.id and isinstance(o, ps.ODE)
+    s = ps.sde(name="one_cpt_sde", params=["ke", "sigma", "v"], states=["central"], outputs=["cp"],
+               routes=["infusion(iv) -> central", "bolus(load) -> central"], drift={"central": "-ke * central"},
+               diffusion={"central": "sigma"}, out={"cp": "central / v"}, particles=1000)
+    assert s._model.id == ps.Equation.from_dsl(W.model_source("c5_one_cpt_sde"))._model.id and isinstance(s, ps.SDE)
