@@ -226,3 +226,88 @@ for wt0, wt1 in [(85.0, 95.0), (64.0, 76.0), (50.0, 58.0)]:
         feat.append(dict(params=p, ops=ops, predictions=[float(z) for z in dsl_features_truth(p, wt0, wt1, doses, infusions, obs)]))
 json.dump(dict(dsl=DSL_FEATURES, cases=feat), open(os.path.join(OUT, "dsl_features.json"), "w"), indent=0)
 print("wrote dsl_features.json")
+
+# ---- hybrid_phage.json: the stiff 6-state phage/bacteria model of the reference's long-horizon ODE regression test
+# (src/simulator/equation/ode/mod.rs:1460-1517 model, :1541-1600 schedule: 1e9-unit infusions over 1.25e-3 h), first
+# 13.3 h of that schedule, integrated piecewise between infusion boundaries with SciPy Radau (rtol 1e-11) --------------
+PHAGE_DSL = """
+name = hybrid_phage
+kind = ode
+params = kep, k12, k21, kdep, kcl_air, kgr, kinf, c50, klysis, burst, ksp, kdp, kn, va
+const eps = 1.0e-12
+const bmax = 1.0e10
+states = plasma, peripheral, airway, bacc, binf, bprot
+derived = phage_air, bacc_pos, binf_pos, bprot_pos, tb, inf_eff
+outputs = cp, bact
+
+infusion(iv) -> plasma
+
+phage_air = 0.5 * (airway + sqrt(airway * airway + eps * eps))
+bacc_pos = 0.5 * (bacc + sqrt(bacc * bacc + eps * eps))
+binf_pos = 0.5 * (binf + sqrt(binf * binf + eps * eps))
+bprot_pos = 0.5 * (bprot + sqrt(bprot * bprot + eps * eps))
+tb = bacc_pos + binf_pos + bprot_pos
+inf_eff = kinf * (phage_air / va) / (1.0 + (phage_air / va) / c50)
+
+dx(plasma) = -(kep + k12 + kdep) * plasma + k21 * peripheral
+dx(peripheral) = k12 * plasma - k21 * peripheral
+dx(airway) = kdep * plasma - kcl_air * airway - inf_eff * bacc_pos + burst * klysis * binf_pos
+dx(bacc) = kgr * bacc_pos * (1.0 - tb / bmax) - inf_eff * bacc_pos - ksp * bacc + kdp * bprot - kn * bacc
+dx(binf) = inf_eff * bacc_pos - klysis * binf
+dx(bprot) = ksp * bacc - kdp * bprot
+
+init(bacc) = 3.0 * pow(10.0, 5.5)
+
+out(cp) = plasma ~ continuous()
+out(bact) = bacc ~ continuous()
+"""
+PHAGE_P = [20.799022436141968, 3.611151695251465, 0.20569434165954592, 3.674600839614868, 98.17452669143677, 2.072104573249817,
+           1.909232258796692e-6, 427933.12072753906, 0.8622971177101135, 1.591451644897461, 4.387639760971069, 0.0917521107196808,
+           1.147785520553589, 12.829959392547607]
+PHAGE_INF = [0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.5, 7.0, 7.5, 8.490833, 8.992917, 9.492917, 9.992917, 10.49292,
+             10.99292, 11.49292]
+PHAGE_INF3 = [12.01458, 13.01542]
+PHAGE_OBS = [0.005, 0.01791667, 0.02208333, 0.03458333, 0.03833333, 0.08458333, 0.18625, 8.991667, 8.995833, 9.010417, 9.074167, 9.166667,
+             12.03958, 13.01375, 13.01792, 13.1925, 13.26875]
+
+
+def phage_truth():
+    kep, k12, k21, kdep, kcl_air, kgr, kinf, c50, klysis, burst, ksp, kdp, kn, va = PHAGE_P
+    eps, bmax = 1e-12, 1e10
+    soft = lambda v: 0.5 * (v + np.sqrt(v * v + eps * eps))
+    infs = [(t, 1e9, 0.00125) for t in PHAGE_INF] + [(t, 3e9, 0.00125) for t in PHAGE_INF3]
+
+    def rhs(t, x, rate):
+        pa, bp, bi, br = soft(x[2]), soft(x[3]), soft(x[4]), soft(x[5])
+        tb = bp + bi + br
+        cair = pa / va
+        ie = kinf * cair / (1.0 + cair / c50)
+        return [-(kep + k12 + kdep) * x[0] + k21 * x[1] + rate, k12 * x[0] - k21 * x[1],
+                kdep * x[0] - kcl_air * x[2] - ie * bp + burst * klysis * bi,
+                kgr * bp * (1.0 - tb / bmax) - ie * bp - ksp * x[3] + kdp * x[5] - kn * x[3], ie * bp - klysis * x[4], ksp * x[3] - kdp * x[5]]
+    pts = sorted(set(PHAGE_OBS) | {b for t, a, d in infs for b in (t, t + d)})
+    x = np.zeros(6)
+    x[3] = 3.0 * 10 ** 5.5
+    t = 0.0
+    out = {}
+    for b in pts:
+        if b > t:
+            rate = sum(a / d for s, a, d in infs if s <= t and b <= s + d)
+            sol = solve_ivp(lambda tt, xx: rhs(tt, xx, rate), (t, b), x, method="Radau", rtol=1e-11, atol=1e-6)
+            x = sol.y[:, -1]
+            t = b
+        if b in PHAGE_OBS:
+            out[b] = (float(x[0]), float(x[3]))
+    return out
+
+
+truth = phage_truth()
+ops = [("infusion", t, 1e9, "iv", 0.00125) for t in PHAGE_INF] + [("infusion", t, 3e9, "iv", 0.00125) for t in PHAGE_INF3]
+preds = []
+for t in PHAGE_OBS:
+    ops.append(("missing_observation", t, "cp")); ops.append(("missing_observation", t, "bact"))
+order = sorted(range(len(PHAGE_OBS)), key=lambda k: PHAGE_OBS[k])
+for k in order:                         # prediction rows follow the event order: by time, cp before bact (insertion order)
+    preds += [truth[PHAGE_OBS[k]][0], truth[PHAGE_OBS[k]][1]]
+json.dump(dict(dsl=PHAGE_DSL, params=PHAGE_P, ops=ops, predictions=preds), open(os.path.join(OUT, "hybrid_phage.json"), "w"), indent=0)
+print("wrote hybrid_phage.json")

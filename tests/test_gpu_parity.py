@@ -834,3 +834,42 @@ def test_particle_filter_converges_to_the_kalman_likelihood(ps, W):
     # first order in dt: a 10x smaller step gives a ~10x smaller bias for every support point
     ratio = err_c / err_f
     assert np.all((ratio > 6.0) & (ratio < 15.0)), (err_c, err_f, ratio)
+
+
+@pytest.mark.parametrize("solver,tol,bar", [("Rodas4", 1e-9, 1e-5), ("Dopri5", 1e-10, 1e-5), ("Sdirk4", 1e-9, 1e-4)])
+def test_stiff_hybrid_phage_model_vs_radau_golden(ps, solver, tol, bar):
+    """The reference's long-horizon stiff regression model (ode/mod.rs:1460-1600: 6 states, soft-plus clamps, logistic
+    growth to 1e10, 25 infusions of 1e9-3e9 units over 1.25e-3 h) through DSL -> CUDA, against SciPy Radau (rtol 1e-11)
+    on 17 observation times x 2 outputs.  Exercises the restart logic at 50 infusion boundaries and the register LU at N = 6."""
+    g = golden("hybrid_phage")
+    eq = ps.Equation.from_dsl(g["dsl"]).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(tol, tol)
+    got = gpu_predictions(ps, eq, [tuple(o) for o in g["ops"]], g["params"])
+    want = np.array(g["predictions"])
+    assert got.shape == want.shape and np.all(np.isfinite(got))
+    err = rel(got, want, 1.0)      # amounts are 1e4 .. 3e9; floor of 1 unit
+    assert err.max() <= bar, (solver, err.max(), int(err.argmax()))
+
+
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Rodas4", "Sdirk4", "TrBdf2"])
+def test_ode_event_times_within_ulps_of_boundaries(ps, solver):
+    """ode/mod.rs:1347-1455: (1) an infusion that ends one ULP after an observation — the loop must keep integrating to the
+    next observation (expected value in closed form); (2) observations 16 ULPs on either side of a bolus time must not
+    error and give 4 predictions."""
+    src = "name = ulp1\nkind = ode\nparams = k\nstates = central\noutputs = cp\ninfusion(iv) -> central\ndx(central) = -k * central\nout(cp) = central ~ continuous()\n"
+    eq = ps.Equation.from_dsl(src).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(1e-8, 1e-8)
+    dur = float(np.nextafter(10.0, 11.0)) - 5.0
+    got = gpu_predictions(ps, eq, [("infusion", 5.0, 100.0, "iv", dur), ("observation", 10.0, 0.0, "cp"), ("observation", 20.0, 0.0, "cp")], [0.5])
+    delivered = 100.0 * (1.0 - math.exp(-2.5)) / 2.5
+    assert got[1] == pytest.approx(delivered * math.exp(-5.0), rel=1e-3)
+    assert got[0] == pytest.approx(delivered, rel=1e-3)
+    src2 = "name = ulp2\nkind = ode\nparams = k\nstates = central\noutputs = cp\nbolus(input_0) -> central\ndx(central) = -k * central\nout(cp) = central ~ continuous()\n"
+    eq2 = ps.Equation.from_dsl(src2).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(1e-8, 1e-8)
+    ulp = float(np.nextafter(12.0, 13.0)) - 12.0
+    ops = [("bolus", 0.0, 200.0, "0"), ("bolus", 12.0, 100.0, "0"), ("missing_observation", 0.0, "cp"), ("missing_observation", 12.0 - 16.0 * ulp, "cp"),
+           ("missing_observation", 12.0 + 16.0 * ulp, "cp"), ("missing_observation", 24.0, "cp")]
+    got = gpu_predictions(ps, eq2, ops, [0.3])
+    assert len(got) == 4 and np.all(np.isfinite(got))
+    before = 200.0 * math.exp(-0.3 * 12.0)
+    bar = 2e-5 if solver == "TrBdf2" else 1e-6          # TR-BDF2 is second order: ~5e-6 at tol 1e-8
+    assert got[0] == 0.0 and got[1] == pytest.approx(before, rel=bar) and got[2] == pytest.approx(before + 100.0, rel=bar)
+    assert got[3] == pytest.approx((before + 100.0) * math.exp(-0.3 * 12.0), rel=bar)
