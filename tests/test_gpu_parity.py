@@ -873,3 +873,35 @@ def test_ode_event_times_within_ulps_of_boundaries(ps, solver):
     bar = 2e-5 if solver == "TrBdf2" else 1e-6          # TR-BDF2 is second order: ~5e-6 at tol 1e-8
     assert got[0] == 0.0 and got[1] == pytest.approx(before, rel=bar) and got[2] == pytest.approx(before + 100.0, rel=bar)
     assert got[3] == pytest.approx((before + 100.0) * math.exp(-0.3 * 12.0), rel=bar)
+
+
+@pytest.mark.parametrize("kernel", ["one_compartment", "one_compartment_with_absorption", "two_compartments_with_absorption"])
+def test_ode_twin_matches_analytical_on_random_dosing(ps, kernel):
+    """tests/ode_optimizations.rs:205-1100 (15 dosing scenarios: single / multiple boluses, oral absorption, overlapping
+    infusions, bolus at an observation time, very fast / slow elimination, rapid absorption) generalised: the ODE twin of a
+    closed-form kernel on randomized timelines, both on the device; reference tolerance 1e-2 relative, here 1e-6."""
+    seed = sum(kernel.encode())
+    rng = np.random.default_rng(seed)
+    absorb = kernel.endswith("with_absorption")
+    subjects = [(f"r{i}", _random_subject(rng, absorb, int(rng.integers(1, 3)))) for i in range(6)]
+    twin = {
+        "one_compartment": ("params = ke, v\nstates = central\n", "bolus(input_0) -> central\ninfusion(input_0) -> central\n",
+                            "dx(central) = -ke * central\n"),
+        "one_compartment_with_absorption": ("params = ka, ke, v\nstates = gut, central\n", "bolus(input_0) -> gut\nbolus(input_1) -> central\ninfusion(input_0) -> central\n",
+                                            "dx(gut) = -ka * gut\ndx(central) = ka * gut - ke * central\n"),
+        "two_compartments_with_absorption": ("params = ke, ka, kcp, kpc, v\nstates = gut, central, peripheral\n",
+                                             "bolus(input_0) -> gut\nbolus(input_1) -> central\ninfusion(input_0) -> central\n",
+                                             "dx(gut) = -ka * gut\ndx(central) = ka * gut - (ke + kcp) * central + kpc * peripheral\n"
+                                             "dx(peripheral) = kcp * central - kpc * peripheral\n"),
+    }[kernel]
+    ode = ps.Equation.from_dsl(f"name = twin_{kernel}\nkind = ode\n{twin[0]}outputs = outeq_0\n{twin[1]}{twin[2]}out(outeq_0) = central / v ~ continuous()\n")
+    ode.with_solver(ps.OdeSolver.Dopri5).with_tolerances(1e-10, 1e-10)
+    ana = ps.Equation.from_dsl(FX.kernel_dsl(kernel))
+    names = FX.KERNEL_PARAMS[kernel]
+    base = {"ke": [0.1, 5.0, 0.001, 0.3], "ka": [1.0, 10.0, 0.5, 2.0], "kcp": [0.3, 1.0, 0.05, 0.2], "kpc": [0.2, 0.5, 0.02, 0.1], "v": [50.0, 10.0, 100.0, 25.0]}
+    spp = np.array([[base[n][k] for n in names] for k in range(4)])      # nominal, very fast, very slow, mixed
+    data = ps.Data([ps.Subject(i, o) for i, o in subjects])
+    pa, offs = ana.predictions_matrix(data, spp)
+    po, _ = ode.predictions_matrix(data, spp)
+    scale = np.maximum(np.abs(pa), 1e-6 * np.abs(pa).max())
+    assert (np.abs(po - pa) / scale).max() <= 1e-6
