@@ -245,27 +245,13 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
 template <class M, int SOLVER>
 __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
                                                 long long spp_ld, const RunOpts& opt, const OutView& out) {
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ncols) return;
-    // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
-    // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
-    const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
     const int nsub = (opt.nsub_limit > 0 && opt.nsub_limit < pop.nsub) ? opt.nsub_limit : pop.nsub;
     Counters cnt;
-    if (opt.diagonal) {
-        // log_likelihood_batch: subject q with parameter row q; a failed simulation scores -inf (mod.rs:134-137)
-        PairCtx<M> c;
-#pragma unroll
-        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + q);
-        M::prologue(c.p);
-        int status = ST_OK;
-        double ll = run_pair<M, SOLVER>(pop, opt, (int)q, c, status, cnt, nullptr, 0);
-        if (status != ST_OK) ll = -psi_inf();
-        if (out.ll) out.ll[q] = ll;
-        flush_counters(out, cnt);
-        return;
-    }
-    for (int subj = blockIdx.y; subj < nsub; subj += gridDim.y) {
+    // one (subject, column slot) pair
+    auto do_pair = [&](int subj, long long q) {
+        // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
+        // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
+        const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
         PairCtx<M> c;
 #pragma unroll
         for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
@@ -287,7 +273,35 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         } else if (out.ll) {
             out.ll[(long long)subj + j * out.ld_ll] = ll;
         }
+    };
+    if (opt.warp_tasks) {
+        // Few support points: a 128-column CTA per subject would idle most lanes, so the warps of a 1-D grid take
+        // (subject, 32-column chunk) tasks in order and a CTA mixes subjects.
+        const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+        const long long nchunk = (ncols + 31) >> 5, ntask = nchunk * (long long)nsub;
+        for (long long task = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += (long long)gridDim.x * wpb) {
+            const long long q = (task % nchunk) * 32 + lane;
+            if (q < ncols) do_pair((int)(task / nchunk), q);
+        }
+        flush_counters(out, cnt);
+        return;
     }
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncols) return;
+    if (opt.diagonal) {
+        // log_likelihood_batch: subject q with parameter row q; a failed simulation scores -inf (mod.rs:134-137)
+        PairCtx<M> c;
+#pragma unroll
+        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + q);
+        M::prologue(c.p);
+        int status = ST_OK;
+        double ll = run_pair<M, SOLVER>(pop, opt, (int)q, c, status, cnt, nullptr, 0);
+        if (status != ST_OK) ll = -psi_inf();
+        if (out.ll) out.ll[q] = ll;
+        flush_counters(out, cnt);
+        return;
+    }
+    for (int subj = blockIdx.y; subj < nsub; subj += gridDim.y) do_pair(subj, q);
     flush_counters(out, cnt);
 }
 

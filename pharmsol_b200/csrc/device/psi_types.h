@@ -137,7 +137,9 @@ struct RunOpts {
     // log_likelihood_batch (likelihood/mod.rs:119-177): thread q evaluates subject q with parameter row q and
     // scores it with the prediction-based residual error models below
     int32_t diagonal;
+    int32_t warp_tasks;       // few support points (< 128): warp w of the 1-D grid takes (subject, 32-column chunk) task w
     int32_t nresid;
+    int32_t pad3_;
     ResidErr resid[PSI_MAX_RESID];
 };
 
