@@ -18,18 +18,21 @@ dev = torch.device("cuda", local)
 os.environ["NCCL_DEBUG"] = "WARN"
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for name, nsub, nspp, kw in [("c1", 40, 1003, {}), ("c2", 64, 2500, dict(solver=ps.OdeSolver.Dopri5, tol=1e-6)), ("c3", 16, 777, {})]:
-    w = W.make(name, nsub=nsub, nspp=nspp)
+for name, nsub, nspp, kw in [("c1", 40, 1003, {}), ("c2", 64, 2500, dict(solver=ps.OdeSolver.Dopri5, tol=1e-6)), ("c3", 16, 777, {}),
+                             ("c5", 6, 130, dict(particles=96))]:
+    w = W.make(name, nsub=nsub, nspp=nspp, **({"particles": kw["particles"]} if "particles" in kw else {}))
     eq, data, ems = H.product_objects(w, device=local)
     if "solver" in kw:
         eq.with_solver(kw["solver"]).with_tolerances(kw["tol"], kw["tol"])
+    if "particles" in kw:      # SDE streams are keyed by the global pair index: sharding must not change psi
+        eq.with_particles(kw["particles"]).with_mode(ps.SdeMode.ParticleFilter).with_seed(99)
     ref = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)          # whole matrix on this GPU, host API
     for peer in (True, False):
         job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=peer)
         fused = getattr(job.sharded, "peer_ptrs", None) is not None
         job.step()
         psi = job.finish().cpu().numpy()
-        same = np.array_equal(psi, ref)
+        same = np.array_equal(psi, ref, equal_nan=True)
         ok = ok and same and (fused == peer)
         print(f"rank {rank} {name} peer_stores={peer} fused={fused} equal_to_single_gpu={same} err={getattr(job.sharded, 'peer_error', None)}", flush=True)
         dist.barrier()
