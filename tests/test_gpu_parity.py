@@ -939,3 +939,19 @@ out(cp) = central / adjusted_v ~ continuous()
     # and the DSL-runtime semantics (derive at the sub-interval end) differ measurably on this fixture
     other = gpu_predictions(ps, ps.Equation.from_dsl(src), ops, p)
     assert rel(other, want, 1e-10).max() > 1e-6
+
+
+def test_assay_error_model_sigma_anchors_on_device(ps, oracle):
+    """data/error_model.rs:1186-1239 literal sigmas (sqrt(26), 2) and the per-observation ErrorPoly override, through the
+    device likelihood."""
+    eq = ps.Equation.from_dsl(FX.kernel_dsl("one_compartment"))
+    p = [0.2, 1.0]
+    s = ps.Subject("a", [("bolus", 0.0, 12.0, "0"), ("observation", 1.0, 20.0, "0")])
+    pred = 12.0 * math.exp(-0.2)
+    for model, sigma in ((ps.AssayErrorModel.additive(ps.ErrorPoly(1.0, 0.0, 0.0, 0.0), 5.0), math.sqrt(26.0)),
+                         (ps.AssayErrorModel.proportional(ps.ErrorPoly(1.0, 0.0, 0.0, 0.0), 2.0), 2.0)):
+        ll = eq.estimate_log_likelihood(s, p, ps.AssayErrorModels().add("outeq_0", model))
+        assert ll == pytest.approx(oracle.lognormpdf(20.0, pred, sigma), rel=1e-13)
+    s2 = ps.Subject("b", [("bolus", 0.0, 12.0, "0"), ("observation_with_error", 1.0, 20.0, "0", (0.5, 0.1, 0.0, 0.0), "none")])
+    ll = eq.estimate_log_likelihood(s2, p, ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(1.0, 0.0, 0.0, 0.0), 0.0)))
+    assert ll == pytest.approx(oracle.lognormpdf(20.0, pred, 2.5), rel=1e-13)

@@ -247,3 +247,19 @@ def test_log_likelihood_batch_semantics(oracle):
     assert np.all(np.isneginf(oracle.log_likelihood_batch(m, d, prm, [None])))
     with pytest.raises(oracle.OracleError):
         oracle.log_likelihood_batch(m, d, prm[:2], [("constant", 1.0, 0.0)])
+
+
+def test_assay_error_model_sigma_anchors(oracle):
+    """data/error_model.rs:1186-1239: additive(ErrorPoly(1,0,0,0), lambda = 5) -> sigma = sqrt(26);
+    proportional(ErrorPoly(1,0,0,0), gamma = 2) -> sigma = 2 (sigma from the OBSERVATION, here 20)."""
+    m = oracle.Model("one_compartment")
+    s = oracle.Subject([("bolus", 0.0, 12.0, "0"), ("observation", 1.0, 20.0, "0")])
+    p = [0.2, 1.0]
+    pred = m.predictions(s, p)[0]
+    for em, sigma in ((("additive", 5.0, (1.0, 0.0, 0.0, 0.0)), math.sqrt(26.0)), (("proportional", 2.0, (1.0, 0.0, 0.0, 0.0)), 2.0)):
+        ll = m.log_likelihood(s, p, oracle.ErrorModels([em]))
+        assert ll == pytest.approx(oracle.lognormpdf(20.0, pred, sigma), rel=1e-15)
+    # per-observation ErrorPoly overrides the model polynomial (error_model.rs:1056-1066)
+    s2 = oracle.Subject([("bolus", 0.0, 12.0, "0"), ("observation_with_error", 1.0, 20.0, "0", (0.5, 0.1, 0.0, 0.0), "none")])
+    ll = m.log_likelihood(s2, p, oracle.ErrorModels([("additive", 0.0, (1.0, 0.0, 0.0, 0.0))]))
+    assert ll == pytest.approx(oracle.lognormpdf(20.0, pred, 0.5 + 0.1 * 20.0), rel=1e-15)
