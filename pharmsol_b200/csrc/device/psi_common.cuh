@@ -47,6 +47,17 @@ PSI_DEV void fill_cov(const PopView& pop, int occ, double t, double* cov) {
     }
 }
 
+// pow(x, c) for the exponents PK models actually use (allometric 0.75 / 0.25, square roots, small integers): square
+// roots and multiplications instead of the ~150-instruction general pow.  sqrt is correctly rounded, so these are
+// within 1.5 ulp — the same class as CUDA's pow (2 ulp) and the reference's libm powf.
+PSI_DEV double pow_half(double x) { return sqrt(x); }
+PSI_DEV double pow_quarter(double x) { return sqrt(sqrt(x)); }
+PSI_DEV double pow_three_quarters(double x) { const double s = sqrt(x); return s * sqrt(s); }
+PSI_DEV double pow_three_halves(double x) { return x * sqrt(x); }
+PSI_DEV double pow_2(double x) { return x * x; }
+PSI_DEV double pow_3(double x) { return (x * x) * x; }
+PSI_DEV double pow_4(double x) { const double q = x * x; return q * q; }
+
 template <int N> struct AtLeast1 { static constexpr int v = N > 0 ? N : 1; };
 
 // Per-pair context shared by the model callbacks.

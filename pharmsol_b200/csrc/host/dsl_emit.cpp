@@ -249,6 +249,16 @@ struct Emitter {
         throw DslError("bad expression", e->pos);
     }
 
+    // pow(x, c) with a literal exponent that has a cheap exact-arithmetic form (device/psi_common.cuh pow_*)
+    static std::string special_pow(const Val& x, const Val& y) {
+        if (!y.is_const || x.is_const) return "";
+        const double c = y.cval;
+        const char* fn = c == 0.5 ? "pow_half" : c == 0.25 ? "pow_quarter" : c == 0.75 ? "pow_three_quarters" : c == 1.5 ? "pow_three_halves"
+                       : c == 2.0 ? "pow_2" : c == 3.0 ? "pow_3" : c == 4.0 ? "pow_4" : nullptr;
+        if (c == 1.0) return x.code;
+        return fn ? std::string("psi::") + fn + "(" + x.code + ")" : "";
+    }
+
     Val binary(const ExprP& e, Scope& s) {
         const std::string& op = e->name;
         Val a = expr(e->args[0], s), b = expr(e->args[1], s);
@@ -286,7 +296,8 @@ struct Emitter {
         if (op == "^") {
             Val x = real(a), y = real(b);
             if (x.is_const && y.is_const) return mkconst(std::pow(x.cval, y.cval), Ty::Real);
-            Val r; r.code = "pow(" + x.code + ", " + y.code + ")"; return r;
+            const std::string sp = special_pow(x, y);
+            Val r; r.code = sp.empty() ? "pow(" + x.code + ", " + y.code + ")" : sp; return r;
         }
         throw DslError("unknown operator `" + op + "`", e->pos);
     }
@@ -321,7 +332,13 @@ struct Emitter {
         if (f == "cos") return unary_real("cos");
         if (f == "tan") return unary_real("tan");
         if (f == "sqrt") return unary_real("sqrt");
-        if (f == "pow") { need(2); Val x = real(a[0]), y = real(a[1]); Val r; r.code = "pow(" + x.code + ", " + y.code + ")"; return r; }
+        if (f == "pow") {
+            need(2);
+            Val x = real(a[0]), y = real(a[1]);
+            if (x.is_const && y.is_const) return mkconst(std::pow(x.cval, y.cval), Ty::Real);
+            const std::string sp = special_pow(x, y);
+            Val r; r.code = sp.empty() ? "pow(" + x.code + ", " + y.code + ")" : sp; return r;
+        }
         if (f == "max" || f == "min") {
             need(2);
             if (a[0].ty == Ty::Int && a[1].ty == Ty::Int) {
