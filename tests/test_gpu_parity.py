@@ -955,3 +955,21 @@ def test_assay_error_model_sigma_anchors_on_device(ps, oracle):
     s2 = ps.Subject("b", [("bolus", 0.0, 12.0, "0"), ("observation_with_error", 1.0, 20.0, "0", (0.5, 0.1, 0.0, 0.0), "none")])
     ll = eq.estimate_log_likelihood(s2, p, ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(1.0, 0.0, 0.0, 0.0), 0.0)))
     assert ll == pytest.approx(oracle.lognormpdf(20.0, pred, 2.5), rel=1e-13)
+
+
+def test_constant_and_fixed_covariates_in_the_kernel_parameters(ps, oracle, H, W):
+    """A covariate with one record, or a fixed (carry-forward) covariate, feeding the kernel parameters of the
+    3-compartment model: same likelihoods as the oracle."""
+    w = W.make("c3", nsub=6, nspp=64)
+    subs = []
+    for k, (sid, ops) in enumerate(w["subjects"]):
+        cov = [o for o in ops if o[0] == "covariate"]
+        rest = [o for o in ops if o[0] != "covariate"]
+        keep = cov[:1] if k % 2 == 0 else cov + [("covariate_fixed", 0, "wt", True)]     # single record | fixed (carry-forward)
+        subs.append((sid, keep + rest))
+    w = dict(w, subjects=subs)
+    eq, data, ems = H.product_objects(w)
+    psi = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    om, od, oe = H.oracle_objects(w)
+    ref = om.log_likelihood_matrix(od, w["support_points"], oe)
+    ll_close(psi, ref, 10, 1e-10)
