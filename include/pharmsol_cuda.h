@@ -187,6 +187,11 @@ int64_t pharmsol_cuda_population_nsubjects(const pcu_population* pop);
 int64_t pharmsol_cuda_population_nobservations(const pcu_population* pop);   /* prediction rows */
 /* prefix sums of per-subject observation counts, nsub+1 entries (ragged prediction layout) */
 int32_t pharmsol_cuda_population_obs_offsets(const pcu_population* pop, int64_t* out);
+/* per prediction row (same order as the rows of pharmsol_cuda_predictions): the Observation the row belongs to —
+ * time, observed value (NaN = missing), output equation, occasion index, censoring (Prediction, likelihood/prediction.rs:18-27).
+ * Any pointer may be NULL. */
+int32_t pharmsol_cuda_population_observation_table(const pcu_population* pop, double* time, double* value, int32_t* outeq,
+                                                   int32_t* occasion, int32_t* censoring);
 int64_t pharmsol_cuda_population_device_bytes(const pcu_population* pop);
 
 /* ---- the hot path ------------------------------------------------------------------------------------- */

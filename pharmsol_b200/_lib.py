@@ -120,6 +120,7 @@ def lib():
         "pharmsol_cuda_population_nobservations": (i64, [vp]),
         "pharmsol_cuda_population_obs_offsets": (i32, [vp, P(i64)]),
         "pharmsol_cuda_population_device_bytes": (i64, [vp]),
+        "pharmsol_cuda_population_observation_table": (i32, [vp, dp, dp, P(i32), P(i32), P(i32)]),
         "pharmsol_cuda_log_likelihood_matrix": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
         "pharmsol_cuda_log_likelihood_matrix_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, i64, vp]),
         "pharmsol_cuda_log_likelihood_matrix_peers": (i32, [vp, vp, vp, vp, i64, i64, P(vp), i32, i64, i64, vp]),
@@ -387,6 +388,15 @@ class Population:
     nsubjects = property(lambda self: lib().pharmsol_cuda_population_nsubjects(self.ptr))
     nobservations = property(lambda self: lib().pharmsol_cuda_population_nobservations(self.ptr))
     device_bytes = property(lambda self: lib().pharmsol_cuda_population_device_bytes(self.ptr))
+
+    def observation_table(self):
+        """time, value (NaN = missing), outeq, occasion, censoring per prediction row."""
+        n = self.nobservations
+        t, v = np.empty(n), np.empty(n)
+        oq, oc, ce = (np.empty(n, dtype=np.int32) for _ in range(3))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        check(lib().pharmsol_cuda_population_observation_table(self.ptr, _dp(t), _dp(v), ip(oq), ip(oc), ip(ce)))
+        return t, v, oq, oc, ce
 
     def obs_offsets(self):
         out = (C.c_int64 * (self.nsubjects + 1))()

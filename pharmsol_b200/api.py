@@ -266,20 +266,52 @@ class EqnKind:
     ODE, Analytical, SDE = 0, 1, 2
 
 
+class Prediction:
+    """likelihood/prediction.rs:18-27."""
+
+    def __init__(self, time, observation, prediction, outeq, occasion, censoring):
+        self._time, self._observation, self._prediction = float(time), observation, float(prediction)
+        self._outeq, self._occasion, self._censoring = int(outeq), int(occasion), censoring
+
+    def time(self):
+        return self._time
+
+    def observation(self):
+        return self._observation
+
+    def prediction(self):
+        return self._prediction
+
+    def outeq(self):
+        return self._outeq
+
+    def occasion(self):
+        return self._occasion
+
+    def censoring(self):
+        return self._censoring
+
+
 class SubjectPredictions:
     """likelihood/subject.rs:19: predictions of one subject for one support point."""
 
-    def __init__(self, times, observations, predictions):
-        self._t, self._o, self._p = times, observations, predictions
+    def __init__(self, predictions):
+        self._predictions = list(predictions)
+
+    def predictions(self):
+        return list(self._predictions)
 
     def flat_predictions(self):
-        return list(self._p)
+        return [p.prediction() for p in self._predictions]
 
     def flat_times(self):
-        return list(self._t)
+        return [p.time() for p in self._predictions]
 
     def flat_observations(self):
-        return list(self._o)
+        return [p.observation() for p in self._predictions]
+
+    def __len__(self):
+        return len(self._predictions)
 
 
 class Equation:
@@ -358,7 +390,10 @@ class Equation:
         data = Data([subject])
         p = np.asarray(parameters, dtype=np.float64).reshape(1, -1)
         pred, _ = self.predictions_matrix(data, p)
-        return SubjectPredictions([], [], pred[:, 0].tolist())
+        t, v, oq, oc, ce = self.population(data, None).observation_table()
+        cens = {0: Censor.NONE, 1: Censor.BLOQ, 2: Censor.ALOQ}
+        return SubjectPredictions(Prediction(t[k], None if v[k] != v[k] else float(v[k]), pred[k, 0], oq[k], oc[k], cens[int(ce[k])])
+                                  for k in range(pred.shape[0]))
 
     def estimate_log_likelihood(self, subject: Subject, parameters, error_models: AssayErrorModels) -> float:
         data = Data([subject])

@@ -325,6 +325,24 @@ int32_t pharmsol_cuda_population_obs_offsets(const pcu_population* pop, int64_t*
     for (size_t i = 0; i < pop->p.flat.obs_offsets.size(); ++i) out[i] = pop->p.flat.obs_offsets[i];
     return PCU_OK;
 }
+int32_t pharmsol_cuda_population_observation_table(const pcu_population* pop, double* time, double* value, int32_t* outeq, int32_t* occasion,
+                                                   int32_t* censoring) {
+    if (!pop) return PCU_ERR_INVALID_ARGUMENT;
+    const auto& f = pop->p.flat;
+    for (size_t oc = 0; oc + 1 < f.ev_offsets.size(); ++oc) {
+        for (int32_t e = f.ev_offsets[oc]; e < f.ev_offsets[oc + 1]; ++e) {
+            const psi::EventRec& r = f.events[(size_t)e];
+            if (psi::ev_kind(r.meta) != psi::EV_OBS || r.obs_row < 0) continue;
+            const size_t row = (size_t)r.obs_row;
+            if (time) time[row] = r.time;
+            if (value) value[row] = psi::ev_has_value(r.meta) ? r.a : std::numeric_limits<double>::quiet_NaN();
+            if (outeq) outeq[row] = psi::ev_index(r.meta);
+            if (occasion) occasion[row] = f.occ_index[oc];
+            if (censoring) censoring[row] = psi::ev_cens(r.meta);
+        }
+    }
+    return PCU_OK;
+}
 int64_t pharmsol_cuda_population_device_bytes(const pcu_population* pop) { return pop ? (int64_t)pop->p.dev.cap : 0; }
 
 // ---- hot path ------------------------------------------------------------------------------------------------

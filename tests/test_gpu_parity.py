@@ -973,3 +973,20 @@ def test_constant_and_fixed_covariates_in_the_kernel_parameters(ps, oracle, H, W
     om, od, oe = H.oracle_objects(w)
     ref = om.log_likelihood_matrix(od, w["support_points"], oe)
     ll_close(psi, ref, 10, 1e-10)
+
+
+def test_estimate_predictions_returns_prediction_records(ps):
+    """Equation::estimate_predictions -> SubjectPredictions of Prediction{time, observation, prediction, outeq, occasion,
+    censoring} (likelihood/prediction.rs:18-27, equation/mod.rs:526-532): rows follow the event order of each occasion."""
+    from benches import workloads
+    eq = ps.Equation.from_dsl(workloads.model_source("c4_mm_effect"))
+    s = (ps.Subject.builder("p").bolus(0.0, 200.0, "load").observation(2.0, 3.5, "effect").missing_observation(1.0, "cp")
+         .censored_observation(4.0, 0.2, "cp", ps.Censor.BLOQ).reset().infusion(0.0, 100.0, "iv", 1.0).observation(0.5, 1.0, "cp").build())
+    sp = eq.estimate_predictions(s, [30.0, 2.0, 30.0, 5.0, 100.0, 3.0])
+    rows = sp.predictions()
+    assert len(sp) == 4
+    assert [r.time() for r in rows] == [1.0, 2.0, 4.0, 0.5]
+    assert [r.outeq() for r in rows] == [0, 1, 0, 0] and [r.occasion() for r in rows] == [0, 0, 0, 1]
+    assert rows[0].observation() is None and rows[1].observation() == 3.5 and rows[2].censoring() == ps.Censor.BLOQ
+    assert all(math.isfinite(r.prediction()) and r.prediction() > 0 for r in rows)
+    assert sp.flat_predictions() == [r.prediction() for r in rows]
