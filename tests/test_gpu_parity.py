@@ -990,3 +990,34 @@ def test_estimate_predictions_returns_prediction_records(ps):
     assert rows[0].observation() is None and rows[1].observation() == 3.5 and rows[2].censoring() == ps.Censor.BLOQ
     assert all(math.isfinite(r.prediction()) and r.prediction() > 0 for r in rows)
     assert sp.flat_predictions() == [r.prediction() for r in rows]
+
+
+def test_sde_with_lag_fa_and_zero_noise_tracks_the_ode(ps, oracle):
+    """SDE event handling (lag, bioavailability, bolus destinations, infusion rates in the drift) with the diffusion switched
+    off: Euler-Maruyama at its 1e-2 tolerance must track the closed form of the same model."""
+    sde = """
+name = sde_lag
+kind = sde
+params = ka, ke, v, tlag, f_oral, s
+states = depot, central
+outputs = cp
+particles = 8
+bolus(oral) -> depot
+infusion(iv) -> central
+lag(oral) = tlag
+fa(oral) = f_oral
+dx(depot) = -ka * depot
+dx(central) = ka * depot - ke * central
+noise(central) = s
+out(cp) = central / v ~ continuous()
+"""
+    ops = [("bolus", 0.0, 100.0, "oral"), ("infusion", 2.0, 50.0, "iv", 1.5), ("bolus", 6.0, 80.0, "oral")] + \
+          [("missing_observation", float(t), "cp") for t in (0.25, 0.5, 1.0, 2.0, 3.0, 3.5, 5.0, 6.5, 7.0, 9.0, 12.0)]
+    p = [1.2, 0.25, 20.0, 0.5, 0.8, 0.0]
+    got = gpu_predictions(ps, ps.Equation.from_dsl(sde), ops, p)
+    ana = ps.Equation.from_dsl("name = a\nkind = analytical\nparams = ka, ke, v, tlag, f_oral, s\nstates = depot, central\noutputs = cp\nbolus(oral) -> depot\n"
+                               "infusion(iv) -> central\nlag(oral) = tlag\nfa(oral) = f_oral\nstructure = one_compartment_with_absorption\n"
+                               "out(cp) = central / v ~ continuous()\n")
+    want = gpu_predictions(ps, ana, ops, p)
+    assert got[0] == 0.0 and got[1] == 0.0                      # nothing absorbed before the lagged dose (t = 0.5: obs sorts first)
+    assert np.max(np.abs(got - want)) <= 0.03 * np.max(want)     # EM at rtol = atol = 1e-2 (sde/mod.rs:172)
