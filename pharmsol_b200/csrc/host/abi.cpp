@@ -105,7 +105,10 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
         cuda_check(cudaEventCreate(&c->c.ev0), "cudaEventCreate");
         cuda_check(cudaEventCreate(&c->c.ev1), "cudaEventCreate");
         c->c.err_ctr.reserve(5 * sizeof(unsigned long long));
-        cuda_check(cudaMallocHost((void**)&c->c.err_host, 5 * sizeof(unsigned long long)), "cudaMallocHost");
+        cuda_check(cudaMallocHost((void**)&c->c.err_host, 16 * sizeof(unsigned long long)), "cudaMallocHost");
+        std::memset(c->c.err_host, 0, 16 * sizeof(unsigned long long));
+        c->c.err_host[8] = ~0ull;
+        cuda_check(cudaMallocHost((void**)&c->c.small_host, Ctx::kSmallIn + Ctx::kSmallOut), "cudaMallocHost");
         *out = c;
         return (int32_t)PCU_OK;
     });
@@ -419,9 +422,25 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
         const int64_t nsub = pop->p.flat.nsub;
         if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
-        c.spp_rows.reserve((size_t)nspp * np * 8);
         c.spp_soa.reserve((size_t)nspp * np * 8);
         c.out.reserve((size_t)nsub * nspp * 8);
+        if (c.small_host && (size_t)nspp * np * 8 <= Ctx::kSmallIn && (size_t)nsub * nspp * 8 <= Ctx::kSmallOut) {
+            // Latency-bound call (an optimiser's cost function: one or a few support points).  Transpose on the host
+            // into pinned memory, one kernel, results and status back through pinned memory, one synchronize.
+            double* in = c.small_host;
+            double* res = c.small_host + Ctx::kSmallIn / 8;
+            for (int64_t j = 0; j < nspp; ++j)
+                for (int32_t k = 0; k < np; ++k) in[(size_t)k * nspp + j] = spp[(size_t)j * np + k];
+            cuda_check(cudaMemcpyAsync(c.spp_soa.p, in, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+            launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, c.out.as<double>(), nsub, nullptr, 0, 0, c.stream, nullptr, true);
+            if (exponentiate) { launch_exp_inplace(c.out.as<double>(), nsub * nspp, c.stream); c.launches += 1; }
+            cuda_check(cudaMemcpyAsync(res, c.out.p, (size_t)nsub * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H psi");
+            cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
+            cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+            std::memcpy(out, res, (size_t)nsub * nspp * 8);
+            return collect(c, code, pair, true);
+        }
+        c.spp_rows.reserve((size_t)nspp * np * 8);
         cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
         launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
         c.launches += 1;

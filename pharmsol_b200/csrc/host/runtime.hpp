@@ -45,7 +45,9 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
-    unsigned long long* err_host = nullptr;   // pinned mirror of err_ctr, filled by an async copy queued behind the kernels
+    unsigned long long* err_host = nullptr;   // pinned: [0..4] mirror of err_ctr filled by an async copy queued behind the kernels, [8..12] reset template
+    double* small_host = nullptr;             // pinned staging for latency-bound calls: [0, kSmallIn) support points SoA, then psi
+    static constexpr size_t kSmallIn = 64u << 10, kSmallOut = 256u << 10;
     DevBuf spp_rows, spp_soa, out, pred, scratch;
     DevBuf col_work, col_idx, col_sort;      // work-balanced column order (ODE): probe counts, permutation, cub scratch
     int64_t launches = 0;
