@@ -169,10 +169,25 @@ int32_t pharmsol_cuda_model_set_particles(pcu_model* m, uint32_t nparticles, uin
                                           int32_t em_mode, double em_dt);
 int32_t pharmsol_cuda_model_set_cov_time(pcu_model* m, int32_t cov_time);
 /* build (or fetch) the device module now; returns the NVRTC log in last_error_message on failure.
- * *source_out (optional): 0 = ahead-of-time (nvcc, linked in), 1 = cubin cache, 2 = NVRTC */
+ * *source_out (optional): 0 = ahead-of-time (nvcc, linked in), 1 = cubin cache, 2 = NVRTC, 3 = .pkm artifact */
 int32_t pharmsol_cuda_model_compile(pcu_ctx* ctx, pcu_model* m, int32_t* source_out);
 /* NVRTC-only: compile to a cubin without touching a device (used by the build step) */
 int32_t pharmsol_cuda_model_precompile_to_cache(pcu_model* m, int32_t solver);
+
+/* ---- CUDA-target model artifact (.pkm) ----------------------------------------------------------------
+ * Counterpart of the native-AoT artifact: compile_module_source_to_aot / load_aot_model / read_aot_model_info
+ * (src/dsl/aot.rs:146-353, symbols src/dsl/compiled_backend_abi.rs:6-33) and RuntimeCompilationTarget /
+ * load_runtime_artifact (src/dsl/runtime.rs:118-137).  One file carries the API version, the model-info JSON, the
+ * run settings, the DSL source and the sm_100a cubin of the psi kernel for each requested solver (NVRTC, no GPU
+ * needed to export).  `solvers` = PCU_SOLVER_* list (ODE models; ignored otherwise); nsolvers = 0 exports the
+ * model's current solver.  A loaded model launches the shipped device code directly (pharmsol_cuda_model_compile
+ * reports source 3); if the artifact was built by another engine version the cubin is ignored and the model is
+ * rebuilt from the source it carries.  Errors: unreadable / corrupt / API-version mismatch -> PCU_ERR_OTHER. */
+int32_t pharmsol_cuda_model_export_artifact(pcu_model* m, const char* path, const int32_t* solvers, int32_t nsolvers);
+int32_t pharmsol_cuda_model_load_artifact(pcu_ctx* ctx, const char* path, pcu_model** out);
+/* read_aot_model_info: JSON {format, api_version, engine, engine_matches, settings, kernels[], model}; returns the
+ * byte count needed (excluding the terminator), -1 on error; writes at most cap - 1 bytes + NUL into buf. */
+int64_t pharmsol_cuda_artifact_info_json(const char* path, char* buf, size_t cap);
 
 /* ---- population: flattened Data resident in HBM ------------------------------------------------------ */
 /* Resolve labels against the model's routes / outputs (equation/mod.rs:192-273, dsl/native.rs:663-770),

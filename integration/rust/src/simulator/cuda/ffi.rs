@@ -47,6 +47,9 @@ extern "C" {
     pub fn pharmsol_cuda_model_set_particles(m: *mut pcu_model, n: u32, seed: u64, sde_mode: i32, em_mode: i32, em_dt: f64) -> i32;
     pub fn pharmsol_cuda_model_set_cov_time(m: *mut pcu_model, mode: i32) -> i32;
     pub fn pharmsol_cuda_model_compile(ctx: *mut pcu_ctx, m: *mut pcu_model, source_out: *mut i32) -> i32;
+    pub fn pharmsol_cuda_model_export_artifact(m: *mut pcu_model, path: *const c_char, solvers: *const i32, nsolvers: i32) -> i32;
+    pub fn pharmsol_cuda_model_load_artifact(ctx: *mut pcu_ctx, path: *const c_char, out: *mut *mut pcu_model) -> i32;
+    pub fn pharmsol_cuda_artifact_info_json(path: *const c_char, buf: *mut c_char, cap: usize) -> i64;
 
     pub fn pharmsol_cuda_population_create(ctx: *mut pcu_ctx, m: *const pcu_model, d: *const pcu_data,
                                            ems: *const pcu_error_model, n: i32, out: *mut *mut pcu_population) -> i32;

@@ -13,6 +13,10 @@ unsafe impl Send for CudaEquation {}
 
 impl CudaEquation {
     pub fn from_dsl(source: &str, device: i32) -> Result<Self, PharmsolError> { /* ctx_create + model_from_dsl (+ info JSON) */ }
+    /// dsl/aot.rs:316-353 `load_aot_model` for the CUDA target: API version + checksum are checked by the library.
+    pub fn from_artifact(path: &std::path::Path, device: i32) -> Result<Self, PharmsolError> { /* ctx_create + pharmsol_cuda_model_load_artifact */ }
+    /// dsl/aot.rs:146-300 `compile_module_source_to_aot`: writes the `.pkm` (NVRTC only, no GPU needed).
+    pub fn export_artifact(&self, path: &std::path::Path, solvers: &[OdeSolver]) -> Result<(), PharmsolError> { /* pharmsol_cuda_model_export_artifact */ }
     pub fn with_solver(self, s: OdeSolver) -> Self      { /* model_set_solver; Bdf -> PCU_SOLVER_RODAS4, Tsit45 -> 1, TrBdf2 -> 3, Esdirk34 -> 2 */ self }
     pub fn with_tolerances(self, rtol: f64, atol: f64) -> Self { /* model_set_solver */ self }
 

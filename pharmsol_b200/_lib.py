@@ -131,6 +131,9 @@ def lib():
         "pharmsol_cuda_psi": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
         "pharmsol_cuda_log_likelihood_batch": (i32, [vp, vp, vp, dp, i64, i32, P(pcu_residual_error_model), i32, dp]),
         "pharmsol_cuda_measure_fp64_peak": (i32, [vp, dp, dp]),
+        "pharmsol_cuda_model_export_artifact": (i32, [vp, C.c_char_p, P(i32), i32]),
+        "pharmsol_cuda_model_load_artifact": (i32, [vp, C.c_char_p, P(vp)]),
+        "pharmsol_cuda_artifact_info_json": (i64, [C.c_char_p, C.c_char_p, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -157,6 +160,16 @@ def _b(s):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def artifact_info(path):
+    import json
+    need = lib().pharmsol_cuda_artifact_info_json(str(path).encode(), None, 0)
+    if need < 0:
+        raise PharmsolError(15, _msg())
+    buf = C.create_string_buffer(need + 1)
+    lib().pharmsol_cuda_artifact_info_json(str(path).encode(), buf, need + 1)
+    return json.loads(buf.value.decode())
 
 
 def device_count():
@@ -342,7 +355,18 @@ class Model:
     def compile(self, ctx):
         src = C.c_int32(-1)
         check(lib().pharmsol_cuda_model_compile(ctx.ptr, self.ptr, C.byref(src)))
-        return {0: "aot", 1: "cubin-cache", 2: "nvrtc"}[src.value]
+        return {0: "aot", 1: "cubin-cache", 2: "nvrtc", 3: "artifact"}[src.value]
+
+    def export_artifact(self, path, solvers=()):
+        arr = (C.c_int32 * max(len(solvers), 1))(*[int(s) for s in solvers])
+        check(lib().pharmsol_cuda_model_export_artifact(self.ptr, str(path).encode(), arr, len(solvers)))
+        return str(path)
+
+    @classmethod
+    def from_artifact(cls, path):
+        ptr = C.c_void_p()
+        check(lib().pharmsol_cuda_model_load_artifact(None, str(path).encode(), C.byref(ptr)))
+        return cls(ptr)
 
     def precompile_to_cache(self, solver=0):
         check(lib().pharmsol_cuda_model_precompile_to_cache(self.ptr, int(solver)))

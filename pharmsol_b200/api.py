@@ -334,6 +334,27 @@ class Equation:
     def _post_init(self):
         pass
 
+    def _restore(self, settings):
+        pass
+
+    @staticmethod
+    def from_artifact(path, device=None):
+        """load_aot_model (dsl/aot.rs:316-353): a model from a CUDA-target `.pkm` artifact; the shipped device code
+        is launched as is, settings (solver, tolerances, particles ...) are the exporter's."""
+        info = _lib.artifact_info(path)
+        eq = Equation.__new__(Equation)
+        eq._model = _lib.Model.from_artifact(path)
+        eq.source, eq.info, eq.device, eq._pops = None, eq._model.info, device, {}
+        eq.__class__ = {0: ODE, 1: Analytical, 2: SDE}[eq._model.kind]
+        eq._post_init()
+        eq._restore(info["settings"])
+        return eq
+
+    def export_artifact(self, path, solvers=()):
+        """compile_module_source_to_aot's output step (dsl/aot.rs:146-300): write the `.pkm` for this model with
+        its current settings; NVRTC only, no GPU needed."""
+        return self._model.export_artifact(path, solvers)
+
     # -- introspection (equation/mod.rs:534-547) ----------------------------------------------------
     def kind(self):
         return self._model.kind
@@ -406,6 +427,9 @@ class Equation:
 
 
 class Analytical(Equation):
+    def _restore(self, st):
+        self._model.set_cov_time(int(st["cov_time"]))
+
     def with_cov_time(self, mode):
         self._model.set_cov_time(mode)
         return self
@@ -414,6 +438,10 @@ class Analytical(Equation):
 class ODE(Equation):
     def _post_init(self):
         self._solver, self._rtol, self._atol = OdeSolver.Dopri5, 1e-4, 1e-4   # RTOL/ATOL ode/mod.rs:40-41
+
+    def _restore(self, st):
+        self._solver, self._rtol, self._atol = int(st["solver"]), float(st["rtol"]), float(st["atol"])
+        self._model.set_solver(self._solver, self._rtol, self._atol)
 
     def with_solver(self, solver):
         self._solver = int(solver)
@@ -438,6 +466,11 @@ class SDE(Equation):
 
     def _apply(self):
         self._model.set_particles(self._np, self._seed, self._mode, self._em, self._dt)
+
+    def _restore(self, st):
+        self._np, self._seed, self._mode = int(st["nparticles"]), int(st["seed"]), int(st["sde_mode"])
+        self._em, self._dt = int(st["em_mode"]), float(st["em_dt"])
+        self._apply()
 
     def with_particles(self, n):
         self._np = int(n)
@@ -537,6 +570,59 @@ def sde(name, params, states, outputs, routes, drift, diffusion, out, particles,
 # ---------------------------------------------------------------------------------------------
 # psi matrix (likelihood/matrix.rs)
 # ---------------------------------------------------------------------------------------------
+class RuntimeCompilationTarget:
+    """dsl/runtime.rs:118-125.  `Jit` = NVRTC in this process; `CudaAot(path)` = export a `.pkm` and reload it (the
+    reference's NativeAot round trip)."""
+    Jit = "jit"
+
+    class CudaAot:
+        def __init__(self, output=None, solvers=()):
+            self.output, self.solvers = output, tuple(solvers)
+
+
+class RuntimeArtifactFormat:
+    """dsl/runtime.rs:129-133"""
+    CudaAot = "cuda-aot"
+
+
+def compile_module_source_to_runtime(source, target=RuntimeCompilationTarget.Jit, device=None):
+    """dsl/runtime.rs:207-245"""
+    eq = Equation.from_dsl(source, device)
+    if isinstance(target, RuntimeCompilationTarget.CudaAot):
+        import os
+        import tempfile
+        path = target.output or os.path.join(tempfile.mkdtemp(prefix="pharmsol_b200_"), f"model_sm_100a_{eq._model.id[:5]}.pkm")
+        eq.export_artifact(path, target.solvers)
+        return Equation.from_artifact(path, device)
+    return eq
+
+
+def compile_module_source_to_aot(source, output, solvers=(), configure=None):
+    """dsl/aot.rs:146-300: DSL source -> `.pkm` on disk.  `configure(equation)` may set solver / tolerances /
+    particles before the device code is generated.  Returns the output path."""
+    eq = Equation.from_dsl(source)
+    if configure is not None:
+        configure(eq)
+    return eq.export_artifact(output, solvers)
+
+
+def load_aot_model(path, device=None):
+    """dsl/aot.rs:316-353"""
+    return Equation.from_artifact(path, device)
+
+
+def load_runtime_artifact(path, fmt=RuntimeArtifactFormat.CudaAot, device=None):
+    """dsl/runtime.rs:247-262"""
+    if fmt != RuntimeArtifactFormat.CudaAot:
+        raise PharmsolError(66, f"unknown artifact format {fmt!r}")
+    return Equation.from_artifact(path, device)
+
+
+def read_aot_model_info(path):
+    """dsl/aot.rs:303-312: metadata only (model info, settings, kernels), no device code loaded."""
+    return _lib.artifact_info(path)
+
+
 def log_likelihood_matrix(equation: Equation, subjects: Data, support_points, error_models: AssayErrorModels, progress: bool = False):
     """likelihood/matrix.rs:52-106.  `support_points`: rows = support points, cols = parameters in
     model order.  Returns an F-order (n_subjects, n_support_points) array of log-likelihoods; the

@@ -1,4 +1,5 @@
 // abi.cpp — the extern "C" surface declared in include/pharmsol_cuda.h.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -206,33 +207,85 @@ int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap) {
 }
 
 // ---- models ----------------------------------------------------------------------------------------------
+static pcu_model* make_model(const std::string& source) {
+    auto* m = new pcu_model();
+    try {
+        m->m.cm = dsl::compile_source(source);
+    } catch (...) { delete m; throw; }
+    m->m.dsl_source = source;
+    std::memset(&m->m.opts, 0, sizeof m->m.opts);
+    m->m.opts.rtol = 1e-4; m->m.opts.atol = 1e-4;            // ode/mod.rs:40-41
+    m->m.opts.h0 = 0.0;
+    m->m.opts.em_dt = 0.05;
+    m->m.opts.seed = 0x5eed5eedULL;
+    m->m.opts.solver = psi::SOLVER_DOPRI5;
+    m->m.opts.cov_time = psi::COVTIME_INTERVAL_END;
+    m->m.opts.max_steps = 200000;
+    m->m.opts.balance = 1;
+    m->m.opts.nparticles = m->m.cm.particles > 0 ? m->m.cm.particles : 1000;
+    m->m.opts.sde_mode = psi::SDE_MEAN_PREDICTION;
+    m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;
+    m->m.info_json = m->m.cm.model_info_json();
+    std::vector<std::pair<int, std::string>> entries;
+    if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 5; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
+    else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
+    m->m.source_cache = m->m.cm.cuda_source(entries, false);
+    return m;
+}
 int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, pcu_model** out) {
     return guarded([&] {
         if (!source || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
-        auto* m = new pcu_model();
+        *out = make_model(std::string(source, len));
+        return (int32_t)PCU_OK;
+    });
+}
+// ---- CUDA-target artifact (.pkm) ------------------------------------------------------------------------------
+int32_t pharmsol_cuda_model_export_artifact(pcu_model* m, const char* path, const int32_t* solvers, int32_t nsolvers) {
+    return guarded([&] {
+        if (!m || !path || nsolvers < 0 || (nsolvers > 0 && !solvers)) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::vector<int> list;
+        if (nsolvers == 0) list.push_back(effective_solver(m->m));
+        for (int i = 0; i < nsolvers; ++i) {
+            if (solvers[i] < 0 || solvers[i] > 4) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+            const int sv = m->m.cm.kind == dsl::ModelKind::Ode ? solvers[i] : 0;
+            if (std::find(list.begin(), list.end(), sv) == list.end()) list.push_back(sv);
+        }
+        write_artifact(m->m, path, list);
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_model_load_artifact(pcu_ctx*, const char* path, pcu_model** out) {
+    return guarded([&] {
+        if (!path || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        ArtifactFile a = read_artifact(path);
+        pcu_model* m = make_model(a.dsl_source);
         try {
-            m->m.cm = dsl::compile_source(std::string(source, len));
-        } catch (...) { delete m; throw; }
-        std::memset(&m->m.opts, 0, sizeof m->m.opts);
-        m->m.opts.rtol = 1e-4; m->m.opts.atol = 1e-4;            // ode/mod.rs:40-41
-        m->m.opts.h0 = 0.0;
-        m->m.opts.em_dt = 0.05;
-        m->m.opts.seed = 0x5eed5eedULL;
-        m->m.opts.solver = psi::SOLVER_DOPRI5;
-        m->m.opts.cov_time = psi::COVTIME_INTERVAL_END;
-        m->m.opts.max_steps = 200000;
-        m->m.opts.balance = 1;
-        m->m.opts.nparticles = m->m.cm.particles > 0 ? m->m.cm.particles : 1000;
-        m->m.opts.sde_mode = psi::SDE_MEAN_PREDICTION;
-        m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;
-        m->m.info_json = m->m.cm.model_info_json();
-        std::vector<std::pair<int, std::string>> entries;
-        if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 5; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
-        else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
-        m->m.source_cache = m->m.cm.cuda_source(entries, false);
+            apply_artifact_settings(a.settings, m->m.opts);
+        } catch (const std::exception&) { delete m; throw PharmsolError(PCU_ERR_OTHER, std::string("artifact ") + path + " has malformed settings"); }
+        // Device code compiled against another engine build (other kernel-parameter layout) is not trusted: the
+        // model then takes the usual registry / cache / NVRTC route from the DSL source it carries.
+        if (a.engine_matches) m->m.artifact_cubins = std::move(a.cubins);
         *out = m;
         return (int32_t)PCU_OK;
     });
+}
+int64_t pharmsol_cuda_artifact_info_json(const char* path, char* buf, size_t cap) {
+    int64_t need = -1;
+    guarded([&] {
+        if (!path) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        ArtifactFile a = read_artifact(path);
+        std::string id;
+        try { id = dsl::compile_source(a.dsl_source).id; } catch (...) {}
+        const std::string js = artifact_info_json(a, id);
+        need = (int64_t)js.size();
+        if (buf && cap > 0) {
+            const size_t n = std::min(js.size(), cap - 1);
+            std::memcpy(buf, js.data(), n);
+            buf[n] = '\0';
+        }
+        return (int32_t)PCU_OK;
+    });
+    return need;
 }
 void pharmsol_cuda_model_destroy(pcu_model* m) { delete m; }
 int32_t pharmsol_cuda_model_kind(const pcu_model* m) { return (int32_t)m->m.cm.kind; }

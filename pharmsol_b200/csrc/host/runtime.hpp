@@ -30,7 +30,7 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-enum KernelSource : int { SRC_AOT = 0, SRC_CACHE = 1, SRC_NVRTC = 2 };
+enum KernelSource : int { SRC_AOT = 0, SRC_CACHE = 1, SRC_NVRTC = 2, SRC_ARTIFACT = 3 };
 struct KernelRef {
     const void* fn = nullptr;      // function pointer (AOT) or cudaKernel_t (runtime-loaded library)
     int source = SRC_AOT;
@@ -63,6 +63,8 @@ struct Model {
     std::string source_cache;                 // generated CUDA C (for inspection)
     std::string info_json;
     std::map<int, KernelRef> kernels;         // by solver id
+    std::string dsl_source;                   // as given to pharmsol_cuda_model_from_dsl (travels in the artifact)
+    std::map<int, std::vector<char>> artifact_cubins;   // device code that arrived in a .pkm artifact, by solver id
     std::mutex mu;
 };
 
@@ -82,6 +84,21 @@ KernelRef get_kernel(Model& m, int solver);
 // NVRTC compile to cubin (no device needed); throws dsl::DslError with the compile log on failure.
 std::vector<char> nvrtc_compile_cubin(const std::string& source, const std::string& name);
 std::string cubin_cache_path(const std::string& id, int solver);
+std::string engine_fingerprint();
+
+// --- CUDA-target model artifact (.pkm), artifact.cpp ---------------------------------------------------
+constexpr uint32_t PKM_API_VERSION = 1;
+enum PkmSection : uint32_t { PKM_INFO = 1, PKM_SOURCE = 2, PKM_SETTINGS = 3, PKM_ENGINE = 4, PKM_CUBIN = 5 };
+struct ArtifactFile {
+    uint32_t api_version = 0;
+    std::string info_json, dsl_source, settings, engine;
+    std::map<int, std::vector<char>> cubins;
+    bool engine_matches = false;
+};
+void write_artifact(Model& m, const std::string& path, const std::vector<int>& solvers);
+ArtifactFile read_artifact(const std::string& path);
+std::string artifact_info_json(const ArtifactFile& a, const std::string& model_id);
+void apply_artifact_settings(const std::string& text, psi::RunOpts& o);
 std::string entry_name(const std::string& id, int solver);
 int effective_solver(const Model& m);
 
