@@ -372,7 +372,7 @@ class Equation:
         return list(self.info["parameters"])
 
     def output_names(self):
-        return list(self.info["outputs"])
+        return [o["name"] for o in self.info["outputs"]]
 
     @property
     def cuda_source(self):

@@ -113,6 +113,9 @@ struct RouteInfo {
     int index = 0;            // dense input slot
     int destination = -1;     // destination state offset
     bool has_lag = false, has_bioavailability = false;   // dsl/model_info.rs route properties
+    int declaration_index = 0;
+    std::string destination_name;
+    bool inject_input_to_destination = true;            // false when dynamics / drift read the route input themselves
 };
 struct ModelLabels {
     std::vector<RouteInfo> routes;

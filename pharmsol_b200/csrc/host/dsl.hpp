@@ -96,6 +96,8 @@ struct CompiledModel {
     ModelKind kind = ModelKind::Ode;
     std::vector<std::string> parameters, derived, covariates, states, outputs;
     std::vector<RouteInfo> routes;
+    std::vector<std::string> covariate_interpolation;            // "" | "linear" | "locf", parallel to `covariates`
+    std::vector<std::pair<std::string, int>> state_decls;       // declared states (arrays once) with their dense offsets
     int state_len = 0, derived_len = 0, output_len = 0, route_len = 0;
     int analytical_kernel = -1;
     int particles = 0;

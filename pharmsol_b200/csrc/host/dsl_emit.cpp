@@ -11,6 +11,7 @@
 //     solvers — the reference has none (Newton uses a linear-RHS trick, ode/closure.rs:360-375).
 // Typing: Int / Real / Bool; integer-valued literals are Int; `/`, `^`, pow are always Real;
 // max/min -> fmax/fmin; Real->Int casts saturate (analyze.rs:2751-2817, rust_backend.rs:277-466).
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -604,12 +605,13 @@ CompiledModel compile_model(const ModelAst& ast_in) {
             throw DslError(std::string("duplicate ") + what + " `" + n + "`");
     };
     for (const auto& p : ast.params) { check_dup(p, "parameter"); c.param_ix[p] = (int)cm.parameters.size(); cm.parameters.push_back(p); }
-    for (const auto& v : ast.covariates) { check_dup(v.name, "covariate"); c.cov_ix[v.name] = (int)cm.covariates.size(); cm.covariates.push_back(v.name); }
+    for (const auto& v : ast.covariates) { check_dup(v.name, "covariate"); c.cov_ix[v.name] = (int)cm.covariates.size(); cm.covariates.push_back(v.name); cm.covariate_interpolation.push_back(v.interpolation); }
     int off = 0;
     for (auto& st : ast.states) {
         check_dup(st.name, "state");
         st.offset = off;
         c.state_by_name[st.name] = st;
+        cm.state_decls.emplace_back(st.name, st.offset);
         if (st.is_array) for (int i = 0; i < st.len; ++i) cm.states.push_back(st.name + "[" + std::to_string(i) + "]");
         else cm.states.push_back(st.name);
         off += st.len;
@@ -661,6 +663,7 @@ CompiledModel compile_model(const ModelAst& ast_in) {
             if (r.has_kind && r.kind == RouteKind::Infusion && (r.lag || r.fa)) throw DslError("lag and bioavailability are bolus-only route properties (route `" + r.name + "`)");
             maxslot = std::max(maxslot, r.index);
             RouteInfo ri; ri.name = r.name; ri.has_kind = r.has_kind; ri.kind = r.kind; ri.index = r.index; ri.destination = r.dest_offset; ri.has_lag = (bool)r.lag; ri.has_bioavailability = (bool)r.fa;
+            ri.declaration_index = r.declaration_index; ri.destination_name = r.dest;
             cm.routes.push_back(ri);
             if (r.lag) cm.has_lag = true;
             if (r.fa) cm.has_fa = true;
@@ -724,6 +727,7 @@ CompiledModel compile_model(const ModelAst& ast_in) {
             if (carries_infusion && !sc_dyn.routes_read.count(r.index))
                 S << "        out[" << r.dest_offset << "] += rate[" << r.index << "];   // infusion(" << r.name << ") -> state " << r.dest_offset << "\n";
         }
+        for (auto& ri : cm.routes) ri.inject_input_to_destination = !sc_dyn.routes_read.count(ri.index);    // model_info.rs:151-154
         S << "    }\n";
         // every state must be touched by the block (validate_state_coverage, analyze.rs:2414-2432)
         std::vector<std::string> touched;
@@ -863,21 +867,47 @@ static std::string json_list(const std::vector<std::string>& v) {
     for (size_t i = 0; i < v.size(); ++i) s += (i ? ", \"" : "\"") + v[i] + "\"";
     return s + "]";
 }
+static std::string camel(const std::string& snake) {
+    std::string out;
+    bool up = true;
+    for (char ch : snake) {
+        if (ch == '_') { up = true; continue; }
+        out += up ? (char)std::toupper((unsigned char)ch) : ch;
+        up = false;
+    }
+    return out;
+}
+
+// The serde JSON of NativeModelInfo (src/dsl/model_info.rs:17-101): enum variants by name (`"Ode"`, `"Locf"`,
+// `"OneCompartment"`), options as null.  `id` (module-cache key) and `analytical_structure` (the DSL spelling) are
+// extra keys a serde reader ignores.
 std::string CompiledModel::model_info_json() const {
     std::ostringstream o;
-    static const char* kinds[3] = {"ode", "analytical", "sde"};
+    static const char* kinds[3] = {"Ode", "Analytical", "Sde"};
+    auto b = [](bool v) { return v ? "true" : "false"; };
     o << "{\"name\": \"" << name << "\", \"kind\": \"" << kinds[(int)kind] << "\", \"id\": \"" << id << "\", \"parameters\": " << json_list(parameters)
-      << ", \"covariates\": " << json_list(covariates) << ", \"states\": " << json_list(states) << ", \"derived\": " << json_list(derived)
-      << ", \"outputs\": " << json_list(outputs) << ", \"routes\": [";
+      << ", \"derived\": " << json_list(derived) << ", \"covariates\": [";
+    for (size_t i = 0; i < covariates.size(); ++i) {
+        const std::string& ip = i < covariate_interpolation.size() ? covariate_interpolation[i] : std::string();
+        o << (i ? ", " : "") << "{\"name\": \"" << covariates[i] << "\", \"index\": " << i << ", \"interpolation\": " << (ip.empty() ? std::string("null") : "\"" + camel(ip) + "\"") << "}";
+    }
+    o << "], \"states\": [";
+    for (size_t i = 0; i < state_decls.size(); ++i)
+        o << (i ? ", " : "") << "{\"name\": \"" << state_decls[i].first << "\", \"offset\": " << state_decls[i].second << "}";
+    o << "], \"routes\": [";
     for (size_t i = 0; i < routes.size(); ++i) {
         const auto& r = routes[i];
-        o << (i ? ", " : "") << "{\"name\": \"" << r.name << "\", \"kind\": " << (r.has_kind ? (r.kind == RouteKind::Bolus ? "\"bolus\"" : "\"infusion\"") : "null")
-          << ", \"index\": " << r.index << ", \"destination_offset\": " << r.destination << ", \"has_lag\": " << (r.has_lag ? "true" : "false")
-          << ", \"has_bioavailability\": " << (r.has_bioavailability ? "true" : "false") << "}";
+        o << (i ? ", " : "") << "{\"name\": \"" << r.name << "\", \"declaration_index\": " << r.declaration_index << ", \"index\": " << r.index << ", \"kind\": "
+          << (r.has_kind ? (r.kind == RouteKind::Bolus ? "\"Bolus\"" : "\"Infusion\"") : "null") << ", \"destination_offset\": " << r.destination
+          << ", \"destination_name\": \"" << r.destination_name << "\", \"has_lag\": " << b(r.has_lag) << ", \"has_bioavailability\": " << b(r.has_bioavailability)
+          << ", \"inject_input_to_destination\": " << b(r.inject_input_to_destination) << "}";
     }
+    o << "], \"outputs\": [";
+    for (size_t i = 0; i < outputs.size(); ++i) o << (i ? ", " : "") << "{\"name\": \"" << outputs[i] << "\", \"index\": " << i << "}";
     o << "], \"state_len\": " << state_len << ", \"derived_len\": " << derived_len << ", \"output_len\": " << output_len << ", \"route_len\": " << route_len
-      << ", \"analytical\": " << (analytical_kernel >= 0 ? std::string("\"") + kKernelNames[analytical_kernel] + "\"" : "null")
-      << ", \"particles\": " << particles << "}";
+      << ", \"analytical\": " << (analytical_kernel >= 0 ? "\"" + camel(kKernelNames[analytical_kernel]) + "\"" : std::string("null"))
+      << ", \"analytical_structure\": " << (analytical_kernel >= 0 ? std::string("\"") + kKernelNames[analytical_kernel] + "\"" : std::string("null"))
+      << ", \"particles\": " << (kind == ModelKind::Sde && particles > 0 ? std::to_string(particles) : std::string("null")) << "}";
     return o.str();
 }
 

@@ -77,7 +77,7 @@ def test_reference_corpus_sources_compile(ps, case):
     eq = ps.Equation.from_dsl(src)
     assert eq.nparams() == len(p)
     info = eq.info
-    assert info["outputs"] == ["cp"]
+    assert info["outputs"] == [{"name": "cp", "index": 0}] and eq.output_names() == ["cp"]
     cu = eq.cuda_source
     assert "PSI_DEFINE_ENTRY" in cu and "psi_engine.cuh" in cu
     assert eq.kind() == {"ode": 0, "ode_full": 0, "analytical": 1, "analytical_full": 1, "sde": 2}[case]
@@ -87,12 +87,26 @@ def test_model_info_mirrors_native_model_info(ps):
     eq = ps.Equation.from_dsl(FX.ODE_FULL_SOURCE)
     info = eq.info
     assert info["parameters"] == ["ka", "ke", "kcp", "kpc", "v", "tlag", "f_oral", "base_depot", "base_central", "base_peripheral"]
-    assert info["covariates"] == ["wt", "renal"]
-    assert info["states"] == ["depot", "central", "peripheral"]
+    # the serde shape of NativeModelInfo (dsl/model_info.rs:17-101), so a Rust caller can deserialize it as is
+    assert info["kind"] == "Ode" and info["analytical"] is None and info["particles"] is None
+    assert info["covariates"] == [{"name": "wt", "index": 0, "interpolation": "Linear"}, {"name": "renal", "index": 1, "interpolation": "Linear"}]
+    assert info["states"] == [{"name": "depot", "offset": 0}, {"name": "central", "offset": 1}, {"name": "peripheral", "offset": 2}]
+    assert info["derived"] == ["adjusted_ke", "adjusted_kcp", "adjusted_v"] and info["derived_len"] == 3
+    assert (info["state_len"], info["output_len"], info["route_len"]) == (3, 1, 2)
     routes = {r["name"]: r for r in info["routes"]}
     # bolus and infusion routes are numbered independently from 0 (metadata.rs:926-957)
     assert routes["oral"]["index"] == 0 and routes["load"]["index"] == 1 and routes["iv"]["index"] == 0
-    assert routes["oral"]["kind"] == "bolus" and routes["iv"]["kind"] == "infusion"
+    assert routes["oral"]["kind"] == "Bolus" and routes["iv"]["kind"] == "Infusion"
+    assert [r["declaration_index"] for r in info["routes"]] == [0, 1, 2]
+    assert routes["oral"]["destination_name"] == "depot" and routes["iv"]["destination_offset"] == 1
+    assert all(r["inject_input_to_destination"] for r in info["routes"])
+    ana = ps.Equation.from_dsl(FX.ANALYTICAL_FULL_SOURCE).info
+    assert ana["kind"] == "Analytical" and ana["analytical"] == "OneCompartmentWithAbsorption"
+    sde = ps.Equation.from_dsl(FX.SDE_SOURCE).info
+    assert sde["kind"] == "Sde" and sde["particles"] == 16
+    explicit = ps.Equation.from_dsl("name = x\nkind = ode\nparams = ke\nstates = c\noutputs = y\ninfusion(iv) -> c\n"
+                                    "dx(c) = -ke * c + 0.5 * rate(iv)\nout(y) = c ~ continuous()\n").info
+    assert explicit["routes"][0]["inject_input_to_destination"] is False
     assert routes["oral"]["has_lag"] and routes["oral"]["has_bioavailability"] and not routes["load"]["has_lag"]
 
 
