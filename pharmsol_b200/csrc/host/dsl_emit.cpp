@@ -11,6 +11,8 @@
 //     solvers — the reference has none (Newton uses a linear-RHS trick, ode/closure.rs:360-375).
 // Typing: Int / Real / Bool; integer-valued literals are Int; `/`, `^`, pow are always Real;
 // max/min -> fmax/fmin; Real->Int casts saturate (analyze.rs:2751-2817, rust_backend.rs:277-466).
+#include <cstring>
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -70,6 +72,31 @@ std::string fmt_int(long long v) { return std::to_string(v) + "LL"; }
 enum DepBits { DEP_T = 1, DEP_COV = 2, DEP_STATE = 4, DEP_RATE = 8, DEP_DERIVED = 16 };
 
 enum class Role { Derive, Dynamics, Outputs, Init, Lag, Fa, Diffusion };
+
+// "did you mean" (analyze.rs:1990-2027): the closest declared name by edit distance, case-insensitive ties first
+static std::string nearest_name(const std::string& want, const std::vector<std::string>& have) {
+    auto lower = [](std::string v) { for (auto& ch : v) ch = (char)std::tolower((unsigned char)ch); return v; };
+    std::string best;
+    size_t best_d = std::max<size_t>(2, want.size() / 3) + 1;
+    for (const auto& h : have) {
+        if (h == want) continue;
+        if (lower(h) == lower(want)) return h;
+        std::vector<size_t> prev(h.size() + 1), cur(h.size() + 1);
+        for (size_t j = 0; j <= h.size(); ++j) prev[j] = j;
+        for (size_t i = 1; i <= want.size(); ++i) {
+            cur[0] = i;
+            for (size_t j = 1; j <= h.size(); ++j)
+                cur[j] = std::min({prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (want[i - 1] == h[j - 1] ? 0 : 1)});
+            std::swap(prev, cur);
+        }
+        if (prev[h.size()] < best_d) { best_d = prev[h.size()]; best = h; }
+    }
+    return best;
+}
+static std::string suggest(const std::string& want, const std::vector<std::string>& have) {
+    const std::string n = nearest_name(want, have);
+    return n.empty() ? std::string() : "\n  suggestion: did you mean `" + n + "`?";
+}
 
 struct Ctx {
     const ModelAst& m;
@@ -167,7 +194,11 @@ struct Emitter {
     }
     int route_slot(const std::string& label, int pos) const {
         for (const auto& r : c.m.routes) if (r.name == label) return r.index;
-        throw DslError("unknown route `" + label + "` in rate(...)", pos);
+        if (!label.empty() && std::all_of(label.begin(), label.end(), [](char ch) { return std::isdigit((unsigned char)ch) != 0; }))
+            throw DslError("bare numeric route labels are not allowed in the DSL; use `input_" + label + "` instead", pos);
+        std::vector<std::string> have;
+        for (const auto& r : c.m.routes) have.push_back(r.name);
+        throw DslError("unknown route `" + label + "` in rate(...)" + suggest(label, have), pos);
     }
     long long const_int(const ExprP& e, Scope& s) {
         Val v = expr(e, s);
@@ -197,7 +228,18 @@ struct Emitter {
         }
         auto di = c.derived_ix.find(n);
         if (di != c.derived_ix.end()) { s.deps |= DEP_DERIVED; Val v; v.code = "d[" + std::to_string(di->second) + "]"; return v; }
-        throw DslError("unknown identifier `" + n + "`", e->pos);
+        for (const auto& r : c.m.routes)
+            if (r.name == n) throw DslError("unknown identifier `" + n + "`\n  help: route inputs are read through `rate(" + n + ")`", e->pos);
+        if (c.output_ix.count(n))
+            throw DslError("unknown identifier `" + n + "`\n  help: outputs are assignment targets inside the `outputs` block and are not available as expression values", e->pos);
+        std::vector<std::string> have;
+        for (const auto& kv : s.locals) have.push_back(kv.first);
+        for (const auto& kv : c.param_ix) have.push_back(kv.first);
+        for (const auto& kv : c.const_ix) have.push_back(kv.first);
+        for (const auto& kv : c.cov_ix) have.push_back(kv.first);
+        for (const auto& kv : c.state_by_name) have.push_back(kv.first);
+        for (const auto& kv : c.derived_ix) have.push_back(kv.first);
+        throw DslError("unknown identifier `" + n + "`" + suggest(n, have), e->pos);
     }
 
     Val expr(const ExprP& e, Scope& s) {
@@ -350,7 +392,7 @@ struct Emitter {
             Val x = real(a[0]), y = real(a[1]);
             Val r; r.code = (f == "max" ? "fmax(" : "fmin(") + x.code + ", " + y.code + ")"; return r;
         }
-        throw DslError("unknown function `" + f + "`", e->pos);
+        throw DslError("unknown function `" + f + "`" + suggest(f, {"abs", "ceil", "exp", "floor", "ln", "log", "log10", "log2", "max", "min", "pow", "round", "sin", "cos", "tan", "sqrt", "rate"}), e->pos);
     }
 
     // ---- forward-mode derivative of a Real-valued expression w.r.t. state offset s.ad_wrt --------
@@ -455,6 +497,14 @@ void collect_targets(const std::vector<Stmt>& ss, std::vector<std::string>& out)
             if (!seen) out.push_back(s.target);
         } else if (s.kind == Stmt::If) { collect_targets(s.then_body, out); collect_targets(s.else_body, out); }
         else if (s.kind == Stmt::For) collect_targets(s.body, out);
+    }
+}
+// output names assigned anywhere in an outputs block (`out(x) = ...` or plain `x = ...`)
+void collect_output_targets(const std::vector<Stmt>& ss, std::vector<std::string>& out) {
+    for (const auto& s : ss) {
+        if (s.kind == Stmt::Assign && (s.callee == "out" || s.callee.empty())) out.push_back(s.target);
+        else if (s.kind == Stmt::If) { collect_output_targets(s.then_body, out); collect_output_targets(s.else_body, out); }
+        else if (s.kind == Stmt::For) collect_output_targets(s.body, out);
     }
 }
 // names of the states touched by `ddt(state) = ...` statements anywhere in a block
@@ -579,6 +629,68 @@ struct BodyEmitter {
     }
 };
 
+// ---- definite assignment (analyze.rs:790-900, 1352-1360, 2334-2411) --------------------------------------------------
+// A derived value may only be read where it has been assigned on every control-flow path: an `if` without `else`
+// and a `for` body (which may run zero times) contribute nothing; `if`/`else` contributes the intersection.
+struct Flow {
+    std::set<std::string> avail;        // derived values readable here
+    std::set<std::string> targets;      // derive / output targets assigned on every path so far
+    std::set<std::string> locals;
+};
+static std::set<std::string> intersect(const std::set<std::string>& a, const std::set<std::string>& b) {
+    std::set<std::string> out;
+    for (const auto& x : a) if (b.count(x)) out.insert(x);
+    return out;
+}
+static void flow_reads(const ExprP& e, const Ctx& c, const Flow& f) {
+    if (!e) return;
+    if (e->kind == Expr::Name) {
+        if (!f.locals.count(e->name) && c.derived_ix.count(e->name) && !f.avail.count(e->name))
+            throw DslError("derived value `" + e->name + "` is not definitely assigned at this point", e->pos);
+        return;
+    }
+    if (e->kind == Expr::Call && e->name == "rate") return;       // the argument is a route label, not a value
+    for (const auto& a : e->args) flow_reads(a, c, f);
+}
+static void flow_stmts(const std::vector<Stmt>& ss, const Ctx& c, Role role, Flow& f) {
+    for (const auto& st : ss) {
+        switch (st.kind) {
+            case Stmt::Let:
+                flow_reads(st.value, c, f);
+                f.locals.insert(st.target);
+                break;
+            case Stmt::Assign: {
+                flow_reads(st.index, c, f);
+                flow_reads(st.value, c, f);
+                const bool plain = st.callee.empty() && !f.locals.count(st.target);
+                if (role == Role::Derive && !st.callee.empty()) throw DslError("derive assignments must target a bare identifier", st.pos);
+                if (role == Role::Derive && plain) { f.avail.insert(st.target); f.targets.insert(st.target); }
+                else if (role == Role::Outputs && (st.callee == "out" || plain)) f.targets.insert(st.target);
+                break;
+            }
+            case Stmt::If: {
+                flow_reads(st.cond, c, f);
+                Flow a = f, b = f;
+                flow_stmts(st.then_body, c, role, a);
+                if (!st.else_body.empty()) {
+                    flow_stmts(st.else_body, c, role, b);
+                    if (role == Role::Derive) f.avail = intersect(a.avail, b.avail);
+                    if (role == Role::Derive || role == Role::Outputs) f.targets = intersect(a.targets, b.targets);
+                }
+                break;
+            }
+            case Stmt::For: {
+                flow_reads(st.lo, c, f);
+                flow_reads(st.hi, c, f);
+                Flow body = f;
+                body.locals.insert(st.var);
+                flow_stmts(st.body, c, role, body);
+                break;
+            }
+        }
+    }
+}
+
 std::string fnv1a_hex(const std::string& s) {
     unsigned long long h = 1469598103934665603ull;
     for (unsigned char ch : s) { h ^= ch; h *= 1099511628211ull; }
@@ -600,15 +712,34 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     Ctx c(ast);
 
     // ---- symbol tables -------------------------------------------------------------------------
-    auto check_dup = [&](const std::string& n, const char* what) {
-        if (c.param_ix.count(n) || c.cov_ix.count(n) || c.state_by_name.count(n) || c.const_ix.count(n))
-            throw DslError(std::string("duplicate ") + what + " `" + n + "`");
+    // Global names (analyze.rs:19-46, 1739-1800): reserved words are refused, every declared name is unique across
+    // parameters / constants / covariates / states / derived / routes / outputs, except that a route and an
+    // output may share a label.
+    static const char* kReserved[] = {"abs", "bioavailability", "carry_forward", "ceil", "ddt", "exp", "floor", "lag", "linear", "ln", "locf", "log",
+                                      "log10", "log2", "max", "min", "noise", "pow", "rate", "round", "sin", "cos", "tan", "sqrt", "t", "time"};
+    std::map<std::string, char> all_names;      // 'p' 'k' 'v' 's' 'd' 'r' 'o'
+    auto declare = [&](const std::string& n, char kind) {
+        for (const char* r : kReserved) if (n == r) throw DslError("`" + n + "` is reserved by the DSL and cannot be used as a symbol name\n  suggestion: rename `" + n + "` to `" + n + "_value`");
+        auto it = all_names.find(n);
+        if (it == all_names.end()) { all_names[n] = kind; return; }
+        const bool overlap_ok = (it->second == 'r' && kind == 'o') || (it->second == 'o' && kind == 'r') || (it->second == 'r' && kind == 'r');
+        if (!overlap_ok) throw DslError("symbol name `" + n + "` collides with existing `" + n + "`");
     };
-    for (const auto& p : ast.params) { check_dup(p, "parameter"); c.param_ix[p] = (int)cm.parameters.size(); cm.parameters.push_back(p); }
-    for (const auto& v : ast.covariates) { check_dup(v.name, "covariate"); c.cov_ix[v.name] = (int)cm.covariates.size(); cm.covariates.push_back(v.name); cm.covariate_interpolation.push_back(v.interpolation); }
+    auto check_dup = [&](const std::string& n, const char* what, char kind) {
+        if (c.param_ix.count(n) || c.cov_ix.count(n) || c.state_by_name.count(n) || c.const_ix.count(n))
+            throw DslError(std::string("duplicate ") + what + " `" + n + "`\n  note: " + what + " `" + n + "` first declared here");
+        declare(n, kind);
+    };
+    auto digits = [](const std::string& t) { return !t.empty() && std::all_of(t.begin(), t.end(), [](char ch) { return std::isdigit((unsigned char)ch) != 0; }); };
+    auto suffix_of = [&](const std::string& label, const char* prefix) -> std::string {      // canonical_numeric_suffix, analyze.rs:2448-2451
+        const size_t n = std::strlen(prefix);
+        return label.compare(0, n, prefix) == 0 && digits(label.substr(n)) ? label.substr(n) : std::string();
+    };
+    for (const auto& p : ast.params) { check_dup(p, "parameter", 'p'); c.param_ix[p] = (int)cm.parameters.size(); cm.parameters.push_back(p); }
+    for (const auto& v : ast.covariates) { check_dup(v.name, "covariate", 'v'); c.cov_ix[v.name] = (int)cm.covariates.size(); cm.covariates.push_back(v.name); cm.covariate_interpolation.push_back(v.interpolation); }
     int off = 0;
     for (auto& st : ast.states) {
-        check_dup(st.name, "state");
+        check_dup(st.name, "state", 's');
         st.offset = off;
         c.state_by_name[st.name] = st;
         cm.state_decls.emplace_back(st.name, st.offset);
@@ -619,7 +750,7 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     cm.state_len = c.state_len = off;
     Emitter em(c);
     for (const auto& kv : ast.constants) {
-        check_dup(kv.first, "constant");
+        check_dup(kv.first, "constant", 'k');
         Scope s;
         Val v = em.expr(kv.second, s);
         if (!v.is_const) throw DslError("constant `" + kv.first + "` is not a compile-time value");
@@ -634,12 +765,22 @@ CompiledModel compile_model(const ModelAst& ast_in) {
         for (auto& t : targets) { bool seen = false; for (auto& d : dnames) if (d == t) seen = true; if (!seen) dnames.push_back(t); }
     }
     for (auto& d : dnames) {
-        if (c.param_ix.count(d) || c.cov_ix.count(d) || c.state_by_name.count(d)) throw DslError("derived `" + d + "` conflicts with another name");
+        if (c.param_ix.count(d)) throw DslError("derived name `" + d + "` collides with primary parameter `" + d + "`");      // analyze.rs:725-748
+        if (c.cov_ix.count(d) || c.state_by_name.count(d)) throw DslError("derived `" + d + "` conflicts with another name");
+        declare(d, 'd');
         c.derived_ix[d] = (int)cm.derived.size();
         cm.derived.push_back(d);
     }
     cm.derived_len = (int)cm.derived.size();
-    for (auto& o : ast.outputs_decl) { if (c.output_ix.count(o)) throw DslError("duplicate output `" + o + "`"); c.output_ix[o] = (int)cm.outputs.size(); cm.outputs.push_back(o); }
+    for (auto& o : ast.outputs_decl) {
+        // validate_output_label_name, analyze.rs:1813-1822
+        if (digits(o)) throw DslError("bare numeric output labels are not allowed in the DSL; use `outeq_" + o + "` instead");
+        const std::string sfx = suffix_of(o, "input_");
+        if (!sfx.empty()) throw DslError("`" + o + "` is a route label and cannot be used as an output target; use `outeq_" + sfx + "` here");
+        if (c.output_ix.count(o)) throw DslError("duplicate output `" + o + "`");
+        declare(o, 'o');
+        c.output_ix[o] = (int)cm.outputs.size(); cm.outputs.push_back(o);
+    }
     cm.output_len = (int)cm.outputs.size();
     if (cm.output_len == 0) throw DslError("model `" + ast.name + "` declares no outputs");
 
@@ -648,13 +789,26 @@ CompiledModel compile_model(const ModelAst& ast_in) {
         bool uses_kinds = false;
         for (auto& r : ast.routes) if (r.has_kind) uses_kinds = true;
         int nb = 0, ni = 0, decl = 0, maxslot = -1;
+        std::map<std::string, std::set<int>> route_kinds;      // label -> kinds seen (-1 = kind-less), analyze.rs:594-628
         for (auto& r : ast.routes) {
+            if (digits(r.name)) throw DslError("bare numeric route labels are not allowed in the DSL; use `input_" + r.name + "` instead");
+            const std::string sfx = suffix_of(r.name, "outeq_");
+            if (!sfx.empty()) throw DslError("`" + r.name + "` is an output label and cannot be used as a route; use `input_" + sfx + "` here");
+            const int rk = r.has_kind ? (int)r.kind : -1;
+            auto seen = route_kinds.find(r.name);
+            if (seen != route_kinds.end() && (rk == -1 || seen->second.count(-1) || seen->second.count(rk))) throw DslError("duplicate route `" + r.name + "`");
+            route_kinds[r.name].insert(rk);
+            declare(r.name, 'r');
             r.declaration_index = decl;
             if (uses_kinds && r.has_kind) r.index = (r.kind == RouteKind::Bolus) ? nb++ : ni++;
             else r.index = decl;
             ++decl;
             auto si = c.state_by_name.find(r.dest);
-            if (si == c.state_by_name.end()) throw DslError("route `" + r.name + "` targets unknown state `" + r.dest + "`");
+            if (si == c.state_by_name.end()) {
+                std::vector<std::string> have;
+                for (const auto& kv : c.state_by_name) have.push_back(kv.first);
+                throw DslError("route `" + r.name + "` targets unknown state `" + r.dest + "`" + suggest(r.dest, have));
+            }
             long long ix = 0;
             Scope s;
             if (r.dest_index) ix = em.const_int(r.dest_index, s);
@@ -672,6 +826,32 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     }
 
     // ---- analytical structure ---------------------------------------------------------------------
+    // ---- definite assignment -------------------------------------------------------------------------------
+    Flow derive_flow;
+    flow_stmts(ast.derive, c, Role::Derive, derive_flow);
+    {
+        auto check_block = [&](const std::vector<Stmt>& ss, Role role) {
+            Flow f;
+            f.avail = derive_flow.avail;
+            flow_stmts(ss, c, role, f);
+            return f;
+        };
+        check_block(ast.dynamics, Role::Dynamics);
+        check_block(ast.init, Role::Init);
+        check_block(ast.diffusion, Role::Diffusion);
+        Flow of = check_block(ast.outputs, Role::Outputs);
+        Flow rf;
+        rf.avail = derive_flow.avail;
+        for (const auto& r : ast.routes) { flow_reads(r.lag, c, rf); flow_reads(r.fa, c, rf); }
+        std::vector<std::string> assigned;
+        collect_output_targets(ast.outputs, assigned);
+        for (const auto& o : cm.outputs) {
+            if (of.targets.count(o)) continue;
+            const bool ever = std::find(assigned.begin(), assigned.end(), o) != assigned.end();
+            if (!ever) throw DslError("output `" + o + "` is declared in `outputs = ...` but never assigned");
+            throw DslError("output `" + o + "` is not definitely assigned on all control-flow paths");
+        }
+    }
     std::vector<std::pair<bool, int>> kp_bind;   // (is_derived, index) per kernel parameter
     if (ast.kind == ModelKind::Analytical) {
         if (ast.structure.empty()) throw DslError("analytical model `" + ast.name + "` does not declare a structure");
@@ -683,7 +863,11 @@ CompiledModel compile_model(const ModelAst& ast_in) {
             auto pi = c.param_ix.find(n);
             auto di = c.derived_ix.find(n);
             if (pi != c.param_ix.end() && di == c.derived_ix.end()) kp_bind.emplace_back(false, pi->second);
-            else if (di != c.derived_ix.end() && pi == c.param_ix.end()) kp_bind.emplace_back(true, di->second);
+            else if (di != c.derived_ix.end() && pi == c.param_ix.end()) {
+                if (!derive_flow.avail.count(n))
+                    throw DslError("derived value `" + n + "` is not definitely assigned on all control-flow paths before analytical structure `" + ast.structure + "` uses it");
+                kp_bind.emplace_back(true, di->second);
+            }
             else throw DslError("analytical structure `" + ast.structure + "` requires `" + n + "` as a parameter or derived value");
         }
     } else if (!ast.structure.empty()) {

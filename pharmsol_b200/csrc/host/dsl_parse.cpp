@@ -1,6 +1,7 @@
 // dsl_parse.cpp — lexer, expression parser and the two surface-form parsers.
 // Grammar references: pharmsol-dsl/src/lexer.rs:10-62, parser.rs:1022-1261 (expressions and
 // precedence), parser.rs:300-1020 (canonical blocks), authoring.rs:362-900 (shorthand lines).
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdlib>
@@ -145,7 +146,11 @@ struct Parser {
         if (take_punct("{")) { skip_nl_only(); a = parse_expr(); skip_nl_only(); expect_punct("}"); }
         else a = parse_expr();
         skip_nl_only();
-        if (!at_ident("else")) throw DslError("conditional expression needs an `else` branch", peek().pos);
+        if (!at_ident("else")) {
+            bool later_else = false;
+            for (int k = 1; k < 64 && peek(k).kind != Tk::End; ++k) if (peek(k).kind == Tk::Ident && peek(k).text == "else") later_else = true;
+            throw DslError(later_else ? "unexpected tokens after `if`/`else` expression" : "conditional expression needs an `else` branch", peek().pos);
+        }
         bump();
         if (at_ident("if")) b = parse_if_expr();
         else if (take_punct("{")) { skip_nl_only(); b = parse_expr(); skip_nl_only(); expect_punct("}"); }
@@ -193,12 +198,29 @@ struct Parser {
     }
 
     // ---- canonical statements (parser.rs:791-1020) ----------------------------------------------
+    bool surface_if = false;     // authoring statement-level `if`: bodies hold plain-variable assignments only (authoring.rs:700-733)
     std::vector<Stmt> parse_stmt_body() {
+        if (surface_if && !at_punct("{")) throw DslError("expected `{` to open `if`/`else` body", peek().pos);
+        if (surface_if) {
+            int depth = 0;
+            bool closed = false;
+            for (size_t k = 0; peek(k).kind != Tk::End; ++k) {
+                if (peek(k).kind != Tk::Punct) continue;
+                if (peek(k).text == "{") ++depth;
+                else if (peek(k).text == "}" && --depth == 0) { closed = true; break; }
+            }
+            if (!closed) throw DslError("unclosed `{` in `if`/`else` body", peek().pos);
+        }
         expect_punct("{");
         std::vector<Stmt> out;
         skip_newlines();
         while (!at_punct("}")) {
-            if (peek().kind == Tk::End) throw DslError("unterminated block", peek().pos);
+            if (peek().kind == Tk::End) throw DslError(surface_if ? "unclosed `{` in `if`/`else` body" : "unterminated block", peek().pos);
+            if (surface_if && peek().kind == Tk::Ident && !at_ident("if") && peek(1).kind == Tk::Punct && peek(1).text == "(")
+                throw DslError("an `if` statement body supports only plain-variable assignments (`x = <expression>`); to make `ddt(...)`, `out(...)`, or "
+                               "`init(...)` conditional, use a conditional equation instead, e.g. `ddt(central) = if (cond) <a> else <b>`", peek().pos);
+            if (surface_if && peek().kind == Tk::Ident && peek(1).kind == Tk::Punct && peek(1).text == "=" && (peek(2).kind == Tk::Newline || peek(2).kind == Tk::End || (peek(2).kind == Tk::Punct && peek(2).text == "}")))
+                throw DslError("expected `name = <expression>`", peek().pos);
             out.push_back(parse_stmt());
             skip_newlines();
         }
@@ -275,6 +297,11 @@ std::string trim(const std::string& s) {
 
 ExprP parse_expr_str(const std::string& s, int base) {
     Parser p(lex(s, base, false));
+    if (p.at_ident("if")) {      // a surface conditional spans the whole right-hand side (authoring.rs:1520-1543)
+        ExprP e = p.parse_if_expr();
+        if (p.peek().kind != Tk::End) throw DslError("unexpected tokens after `if`/`else` expression", p.peek().pos);
+        return e;
+    }
     ExprP e = p.parse_expr();
     if (p.peek().kind != Tk::End) throw DslError("unexpected trailing tokens `" + p.peek().text + "`", p.peek().pos);
     return e;
@@ -364,6 +391,7 @@ ModelAst parse_authoring(const std::string& src) {
     bool explicit_kind = false;
     std::map<std::string, std::pair<ExprP, ExprP>> route_mods;   // route -> (lag, fa)
     std::set<std::string> declared_outputs;
+    std::vector<std::string> explicit_outputs, inferred_outputs;   // `outputs = ...` items; targets of out(...) seen before any declaration
     // ---- physical lines -> logical lines (authoring.rs: a statement continues while a `{` / `(` / `[` is open,
     // and an `else` that starts the next non-trivial line continues an `if`); comments are stripped per
     // physical line, offsets are kept for diagnostics
@@ -418,9 +446,11 @@ ModelAst parse_authoring(const std::string& src) {
 
         if (t.compare(0, 2, "if") == 0 && (t.size() == 2 || !(std::isalnum((unsigned char)t[2]) || t[2] == '_'))) {
             Parser p(lex(t, base, true));
-            m.derive.push_back(p.parse_stmt());
+            p.surface_if = true;
+            Stmt st = p.parse_stmt();
             p.skip_nl_only();
-            if (p.peek().kind != Tk::End) throw DslError("unexpected trailing tokens `" + p.peek().text + "` after `if` statement", p.peek().pos);
+            if (p.peek().kind != Tk::End) throw DslError("unexpected tokens after `if`/`else` statement: `" + p.peek().text + "`", p.peek().pos);
+            m.derive.push_back(st);
             continue;
         }
         const size_t arrow = find_top_level(t, "->", false);
@@ -475,7 +505,17 @@ ModelAst parse_authoring(const std::string& src) {
                 m.derived_decl.push_back(s);
             }
         }
-        else if (lhs == "outputs") { for (auto& s : split_commas(rhs)) { if (!is_label(s)) throw DslError("bad output `" + s + "`", base); m.outputs_decl.push_back(s); declared_outputs.insert(s); } }
+        else if (lhs == "outputs") {
+            // an `outputs = ...` line that follows inferred `out(...)` targets still has to cover them
+            for (auto& s : split_commas(rhs)) { if (!is_label(s)) throw DslError("bad output `" + s + "`", base); explicit_outputs.push_back(s); }
+            for (auto& o : inferred_outputs) {
+                bool ok = false;
+                for (auto& e : explicit_outputs) ok = ok || e == o;
+                if (!ok) throw DslError("output `" + o + "` is not declared in `outputs = ...`", base);
+            }
+            if (!inferred_outputs.empty()) { m.outputs_decl.clear(); declared_outputs.clear(); inferred_outputs.clear(); }
+            for (auto& s : split_commas(rhs)) if (!declared_outputs.count(s)) { m.outputs_decl.push_back(s); declared_outputs.insert(s); }
+        }
         else if (lhs == "particles") { m.particles = (int)std::strtol(rhs.c_str(), nullptr, 10); }
         else if (lhs == "function") throw DslError("`function = ...` has been renamed to `structure = ...`", base);
         else if (lhs == "structure") { m.structure = rhs; }
@@ -499,10 +539,17 @@ ModelAst parse_authoring(const std::string& src) {
                 else m.dynamics.push_back(s);
             } else if (callee == "out") {
                 if (!is_label(arg)) throw DslError("bad output label `" + arg + "`", base);
-                if (!m.outputs_decl.empty() && !declared_outputs.count(arg)) throw DslError("output `" + arg + "` is not declared in `outputs = ...`", base);
-                if (!declared_outputs.count(arg)) { declared_outputs.insert(arg); m.outputs_decl.push_back(arg); }
+                if (arg.compare(0, 6, "input_") == 0 && arg.size() > 6 && std::all_of(arg.begin() + 6, arg.end(), [](char ch) { return std::isdigit((unsigned char)ch) != 0; }))
+                    throw DslError("`" + arg + "` is a route label and cannot be used as an output; use `outeq_" + arg.substr(6) + "` here", base);
+                if (!explicit_outputs.empty() && !declared_outputs.count(arg)) throw DslError("output `" + arg + "` is not declared in `outputs = ...`", base);
+                if (!declared_outputs.count(arg)) { declared_outputs.insert(arg); m.outputs_decl.push_back(arg); inferred_outputs.push_back(arg); }
                 const size_t tilde = find_top_level(rhs, "~", false);     // `~ continuous()` annotation
-                if (tilde != std::string::npos) rhs = trim(rhs.substr(0, tilde));
+                if (tilde != std::string::npos) {
+                    std::string ann = trim(rhs.substr(tilde + 1)), squeezed;
+                    for (char ch : ann) if (!std::isspace((unsigned char)ch)) squeezed.push_back(ch);
+                    if (squeezed != "continuous()") throw DslError("expected the output annotation `continuous()`, found `" + ann + "`", base);
+                    rhs = trim(rhs.substr(0, tilde));
+                }
                 Stmt s; s.kind = Stmt::Assign; s.pos = base; s.callee = "out"; s.target = arg;
                 s.value = parse_expr_str(rhs, rbase);
                 m.outputs.push_back(s);
@@ -526,7 +573,7 @@ ModelAst parse_authoring(const std::string& src) {
                 // lag / bioavailability are bolus-only; a same-named bolus route takes them
                 bool has_bolus = false;
                 for (auto& q : m.routes) if (q.name == kv.first && q.kind == RouteKind::Bolus) has_bolus = true;
-                if (!has_bolus) throw DslError("DSL authoring does not allow lag/bioavailability on infusion route `" + r.name + "`");
+                if (!has_bolus) throw DslError(std::string("DSL authoring does not allow `") + (kv.second.first ? "lag" : "bioavailability") + "` on infusion route `" + r.name + "`");
                 continue;
             }
             r.lag = kv.second.first; r.fa = kv.second.second; found = true;
@@ -540,6 +587,18 @@ ModelAst parse_authoring(const std::string& src) {
         else m.kind = ModelKind::Ode;
     }
     if (m.name.empty()) throw DslError("missing `name = <identifier>`");
+    if (!m.derived_decl.empty()) {      // authoring.rs:1010-1027: with a `derived = ...` line every derive target must be listed
+        std::vector<const Stmt*> stack;
+        for (const auto& s : m.derive) stack.push_back(&s);
+        while (!stack.empty()) {
+            const Stmt* s = stack.back(); stack.pop_back();
+            if (s->kind == Stmt::Assign && s->callee.empty() && std::find(m.derived_decl.begin(), m.derived_decl.end(), s->target) == m.derived_decl.end())
+                throw DslError("derived value `" + s->target + "` is not declared in `derived = ...`", s->pos);
+            for (const auto& q : s->then_body) stack.push_back(&q);
+            for (const auto& q : s->else_body) stack.push_back(&q);
+            for (const auto& q : s->body) stack.push_back(&q);
+        }
+    }
     return m;
 }
 
@@ -594,7 +653,7 @@ ModelAst parse_canonical(const std::string& src) {
             while (!p.at_punct("}")) {
                 StateDecl d; d.name = p.expect_ident();
                 if (p.take_punct("[")) {
-                    if (p.peek().kind != Tk::Number) throw DslError("expected array length", p.peek().pos);
+                    if (p.peek().kind != Tk::Number) throw DslError("state array size must be an integer constant", p.peek().pos);
                     d.len = (int)p.bump().num; d.is_array = true;
                     p.expect_punct("]");
                 }
