@@ -348,7 +348,12 @@ class Equation:
         eq.__class__ = {0: ODE, 1: Analytical, 2: SDE}[eq._model.kind]
         eq._post_init()
         eq._restore(info["settings"])
+        eq._from_artifact = True
         return eq
+
+    def backend(self):
+        """CompiledRuntimeModel::backend (dsl/runtime.rs): which route produced the device code of this model."""
+        return RuntimeBackend.CudaAot if getattr(self, "_from_artifact", False) else RuntimeBackend.Jit
 
     def export_artifact(self, path, solvers=()):
         """compile_module_source_to_aot's output step (dsl/aot.rs:146-300): write the `.pkm` for this model with
@@ -578,6 +583,12 @@ class RuntimeCompilationTarget:
     class CudaAot:
         def __init__(self, output=None, solvers=()):
             self.output, self.solvers = output, tuple(solvers)
+
+
+class RuntimeBackend:
+    """dsl/mod.rs RuntimeBackend"""
+    Jit = "jit"
+    CudaAot = "cuda-aot"
 
 
 class RuntimeArtifactFormat:

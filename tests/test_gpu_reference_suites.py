@@ -125,6 +125,34 @@ def test_corpus_backends_agree(ps, oracle, case, tmp_path):
         assert np.max(np.abs(a - want) / np.maximum(np.abs(want), 1e-8)) <= bar
 
 
+# ---- tests/bimodal_ke_entrypoint_matrix.rs + tests/support/bimodal_ke.rs ------------------------------------------------
+BIMODAL_KE = ("name = bimodal_ke\nkind = ode\n\nparams = ke, v\nstates = central\noutputs = cp\n\ninfusion(iv) -> central\n\n"
+              "dx(central) = -ke * central\n\nout(cp) = central / v ~ continuous()\n")
+
+
+def test_bimodal_ke_entrypoint_matrix(ps, tmp_path):
+    """Three ways to the same runtime model (bimodal_ke.rs:278-330): runtime Jit, runtime AOT round trip, direct AOT
+    export + load_runtime_artifact; each must reproduce the reference predictions (here the closed form)."""
+    times = (0.5, 1.0, 2.0, 3.0, 4.0, 6.0, 8.0)
+    ke, v = 1.2, 50.0
+    ops = [("infusion", 0.0, 500.0, "iv", 0.5)] + [("missing_observation", t, "cp") for t in times]
+    want = np.array([1000.0 / ke * (1.0 - math.exp(-ke * 0.5)) * math.exp(-ke * (t - 0.5)) / v for t in times])
+    tight = lambda e: e.with_tolerances(1e-11, 1e-11)      # noqa: E731
+    jit = tight(ps.compile_module_source_to_runtime(BIMODAL_KE, ps.RuntimeCompilationTarget.Jit))
+    assert jit.backend() == ps.RuntimeBackend.Jit
+    path = ps.compile_module_source_to_aot(BIMODAL_KE, tmp_path / "bimodal-ke-direct-aot.pkm", configure=tight)
+    direct = ps.load_runtime_artifact(path, ps.RuntimeArtifactFormat.CudaAot)
+    runtime_aot = tight(ps.compile_module_source_to_runtime(BIMODAL_KE, ps.RuntimeCompilationTarget.CudaAot(tmp_path / "bimodal-ke-runtime-aot.pkm")))
+    assert direct.backend() == runtime_aot.backend() == ps.RuntimeBackend.CudaAot
+    got = [_preds(ps, m, ops, [ke, v]) for m in (jit, direct, runtime_aot)]
+    for g in got:
+        assert np.max(np.abs(g - want)) <= 1e-9
+    assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], got[2])
+    # numeric data labels reach the same model only through the input_<n> / outeq_<n> aliases, never by position
+    with pytest.raises(ps.PharmsolError):
+        _preds(ps, jit, [("infusion", 0.0, 500.0, "0", 0.5), ("missing_observation", 1.0, "cp")], [ke, v])
+
+
 def test_full_feature_public_shape(ps):
     """full_feature_dsl_backend_parity.rs:26-134"""
     ode = ps.Equation.from_dsl(FX.ODE_FULL_SOURCE).info
