@@ -478,20 +478,32 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         c.spp_soa.reserve((size_t)nspp * np * 8);
         c.out.reserve((size_t)nsub * nspp * 8);
         if (c.small_host && (size_t)nspp * np * 8 <= Ctx::kSmallIn && (size_t)nsub * nspp * 8 <= Ctx::kSmallOut) {
-            // Latency-bound call (an optimiser's cost function: one or a few support points).  Transpose on the host
-            // into pinned memory, one kernel, results and status back through pinned memory, one synchronize.
+            // Latency-bound call (an optimiser's cost function: one or a few support points).  Support points are
+            // transposed on the host into pinned memory; results and status come back through pinned memory with one
+            // synchronize; the status reset for the NEXT call is queued after this one has been read back, off the
+            // critical path.  For the very smallest calls (<= 2 KB each way) the kernel reads the support points and
+            // stores psi directly in the pinned host buffer (unified addressing), which removes both DMA copies;
+            // measured on the 32 x 64 criterion shapes, beyond a few KB the copy engines are faster than PCIe stores
+            // from the SMs (profiles/r01_tuning.md).
             double* in = c.small_host;
             double* res = c.small_host + Ctx::kSmallIn / 8;
             for (int64_t j = 0; j < nspp; ++j)
                 for (int32_t k = 0; k < np; ++k) in[(size_t)k * nspp + j] = spp[(size_t)j * np + k];
-            cuda_check(cudaMemcpyAsync(c.spp_soa.p, in, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
-            launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, c.out.as<double>(), nsub, nullptr, 0, 0, c.stream, nullptr, true);
+            constexpr size_t kInPlace = 2048;
+            const bool in_place_in = (size_t)nspp * np * 8 <= kInPlace;
+            const bool in_place_out = !exponentiate && (size_t)nsub * nspp * 8 <= kInPlace;
+            if (!in_place_in) cuda_check(cudaMemcpyAsync(c.spp_soa.p, in, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+            launch_psi(c, m->m, pop->p, in_place_in ? in : c.spp_soa.as<double>(), nspp, nspp, in_place_out ? res : c.out.as<double>(), nsub, nullptr, 0, 0,
+                       c.stream, nullptr, true);
             if (exponentiate) { launch_exp_inplace(c.out.as<double>(), nsub * nspp, c.stream); c.launches += 1; }
-            cuda_check(cudaMemcpyAsync(res, c.out.p, (size_t)nsub * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H psi");
+            if (!in_place_out) cuda_check(cudaMemcpyAsync(res, c.out.p, (size_t)nsub * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H psi");
             cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
             cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
             std::memcpy(out, res, (size_t)nsub * nspp * 8);
-            return collect(c, code, pair, true);
+            const int32_t rc = collect(c, code, pair, true);
+            cuda_check(cudaMemcpyAsync(c.err_ctr.p, c.err_host + 8, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream), "reset status");
+            c.status_clean_on = c.stream;
+            return rc;
         }
         c.spp_rows.reserve((size_t)nspp * np * 8);
         cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
