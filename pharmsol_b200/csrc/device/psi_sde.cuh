@@ -148,6 +148,18 @@ struct SdeStep {
 #pragma unroll
         for (int k = 0; k < NS; ++k) x[k] = fma(dx[k], dt, fma(g[k] * (double)z[k], sqdt, x[k]));
     }
+    // The full step y1 and the first half step of y2 both start from (t, x): one drift / diffusion evaluation serves
+    // both (the reference evaluates it twice with identical arguments, em.rs:134-150).
+    PSI_DEV void em_first(double t, double dt, double sq, double sqh, const double* x, double* y1, double* y2, const float* z) {
+        double dx[NS], g[NS];
+        eval(t, x, dx, g);
+        const double hdt = dt * 0.5;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            y1[k] = fma(dx[k], dt, fma(g[k] * (double)z[k], sq, x[k]));
+            y2[k] = fma(dx[k], hdt, fma(g[k] * (double)z[NS + k], sqh, x[k]));
+        }
+    }
     // em.rs:134-167
     PSI_DEV void solve_reference(double t0, double tf, double* x, NormalStream& rng, Counters& cnt) {
         double t = t0, dt = 0.1;
@@ -155,15 +167,12 @@ struct SdeStep {
         while (t < tf) {
             if (++guard > 4000000) break;
             double y1[NS], y2[NS];
-#pragma unroll
-            for (int k = 0; k < NS; ++k) { y1[k] = x[k]; y2[k] = x[k]; }
             float z[4 * ((3 * NS + 3) / 4)];
             rng.template fill<3 * NS>(z);                     // three INDEPENDENT draws per state (em.rs:104-120)
             const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
-            em_step(t, dt, sq, y1, z);
-            em_step(t, dt * 0.5, sqh, y2, z + NS);
+            em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
             em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
-            cnt.evals += 3;
+            cnt.evals += 3;                                  // algorithmic count (the reference evaluates the pair three times)
             // err only steers dt: the weight 1/tol uses the one-MUFU reciprocal and the new step the FP32 rsqrt
             double err = 0.0;
 #pragma unroll
@@ -206,15 +215,12 @@ struct SdeStep {
                 t = t0; dt = 0.1; guard = 0; active = true;
             }
             double y1[NS], y2[NS];
-#pragma unroll
-            for (int q = 0; q < NS; ++q) { y1[q] = x[q]; y2[q] = x[q]; }
             float z[4 * ((3 * NS + 3) / 4)];
             rng.template fill<3 * NS>(z);
             const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
-            em_step(t, dt, sq, y1, z);
-            em_step(t, dt * 0.5, sqh, y2, z + NS);
+            em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
             em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
-            cnt.evals += 3;
+            cnt.evals += 3;                                  // algorithmic count (the reference evaluates the pair three times)
             double err = 0.0;
 #pragma unroll
             for (int q = 0; q < NS; ++q) {
