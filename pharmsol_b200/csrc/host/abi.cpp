@@ -509,15 +509,26 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
         launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
         c.launches += 1;
-        // Pipeline over column chunks: psi is column-major, so a block of columns is one contiguous slab; chunk k is
-        // copied device -> host on the copy stream while chunk k+1 is computed.  Chunks of >= 32 MB, at most 8.
+        // Pipeline over column chunks: psi is column-major, so a block of columns is one contiguous slab; a chunk is
+        // copied device -> host on the copy stream while the next one is computed, and only the LAST copy is exposed.
+        //  * closed-form models (kernel short next to the copy): up to 16 equal chunks of >= 2 MB and >= 128 columns —
+        //    for a 1000 x 1000 one-compartment matrix the 8 MB copy-back is otherwise longer than the kernel;
+        //  * adaptive ODE / SDE models (kernel long next to the copy): every extra launch costs a probe + sort of the
+        //    work-balanced column order and a kernel tail, so two chunks, 7/8 + 1/8 of the columns: the big copy hides
+        //    behind the small chunk's compute and the exposed copy is 1/8 of the matrix (profiles/r01_tuning.md).
         const int64_t bytes = nsub * nspp * 8;
-        int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(8, bytes / (32ll << 20)));
-        if (nspp < nchunk * 1024) nchunk = 1;
-        const int64_t per = (nspp + nchunk - 1) / nchunk;
-        for (int k = 0; k < nchunk; ++k) {
-            const int64_t c0 = k * per, c1 = std::min<int64_t>(nspp, c0 + per);
-            if (c1 <= c0) break;
+        std::vector<int64_t> cuts{0};
+        if (m->m.cm.kind == dsl::ModelKind::Analytical) {
+            int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(Ctx::kMaxChunks, bytes / (2ll << 20)));
+            nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, nspp / 128));
+            const int64_t per = ((nspp + nchunk - 1) / nchunk + 127) / 128 * 128;      // chunk starts stay 1 KB aligned in the SoA rows
+            for (int64_t c0 = per; c0 < nspp; c0 += per) cuts.push_back(c0);
+        } else if (bytes >= (16ll << 20) && nspp >= 8192) {
+            cuts.push_back((nspp - nspp / 8) / 128 * 128);
+        }
+        cuts.push_back(nspp);
+        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+            const int64_t c0 = cuts[k], c1 = cuts[k + 1];
             double* slab = c.out.as<double>() + c0 * nsub;
             launch_psi(c, m->m, pop->p, c.spp_soa.as<double>() + c0, c1 - c0, nspp, slab, nsub, nullptr, 0, c0, c.stream, nullptr, k == 0);
             if (exponentiate) { launch_exp_inplace(slab, nsub * (c1 - c0), c.stream); c.launches += 1; }

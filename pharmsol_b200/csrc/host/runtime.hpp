@@ -41,7 +41,8 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t chunk_ev[kMaxChunks] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
