@@ -364,6 +364,38 @@ def test_first_error_aborts_like_matrix_rs(ps, W, H):
     assert e.value.code == 12 and e.value.pair == 0 + 1 * 2     # first failing pair: subject 0, support point 1
 
 
+def test_first_error_in_a_later_chunk_of_a_pipelined_host_call(ps):
+    """Host calls are pipelined over column chunks (closed-form models: up to 16 equal chunks; adaptive ODE models:
+    7/8 + 1/8 of the columns).  The first failing pair is reported with its GLOBAL index wherever it falls, the columns
+    before and after it are still evaluated, and two failures report the smaller pair (matrix.rs:96-104)."""
+    ops = [("bolus", 0.0, 100.0, "0")] + [("observation", float(t), 50.0 / t, "0") for t in (1, 2, 4)]
+    nsub = 600
+    data = ps.Data([ps.Subject(f"s{i}", ops) for i in range(nsub)])
+    em = ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0))
+    # closed form: 600 x 2048 x 8 B = 9.8 MB -> 4 chunks of 512 columns
+    eq = ps.Equation.from_dsl(FX.kernel_dsl("two_compartments"))
+    spp = np.tile(np.array([[0.1, 3.0, 1.0, 1.0]]), (2048, 1)) * (1.0 + 1e-4 * np.arange(2048)[:, None])
+    good = ps.log_likelihood_matrix(eq, data, spp, em)
+    assert np.all(np.isfinite(good))
+    for bad_cols in ([1500], [1900, 700], [2047]):
+        bad = spp.copy()
+        bad[bad_cols] = [1.0, -3.0, 1.5, 1.0]   # (ke + kcp + kpc)^2 < 4 ke kpc: imaginary roots
+        with pytest.raises(ps.PharmsolError) as e:
+            ps.log_likelihood_matrix(eq, data, bad, em)
+        assert e.value.code == 12 and e.value.pair == 0 + min(bad_cols) * nsub
+    # adaptive ODE: 600 x 8192 x 8 B = 39 MB -> two chunks (7168 + 1024 columns); a failure in the small tail chunk
+    src = ("name = chunk_ode\nkind = ode\nparams = ke, v\nstates = central\noutputs = outeq_0\nbolus(input_0) -> central\n"
+           "dx(central) = -ke * central\nout(outeq_0) = central / v ~ continuous()\n")
+    eo = ps.Equation.from_dsl(src)
+    spo = np.column_stack([0.1 + 1e-5 * np.arange(8192), np.full(8192, 2.0)])
+    ok = ps.log_likelihood_matrix(eo, data, spo, em)
+    assert np.all(np.isfinite(ok))
+    spo[8000, 0] = float("nan")
+    with pytest.raises(ps.PharmsolError) as e:
+        ps.log_likelihood_matrix(eo, data, spo, em)
+    assert e.value.pair == 0 + 8000 * nsub
+
+
 def test_wrong_parameter_count_and_unknown_labels(ps, W, H):
     w = W.make("c1", nsub=2, nspp=4)
     eq, data, ems = H.product_objects(w)
