@@ -238,6 +238,10 @@ int32_t pharmsol_cuda_log_likelihood_matrix_peers(pcu_ctx* ctx, pcu_model* m, pc
                                                   double* const* out_full_peers, int32_t npeers, int64_t ld_out,
                                                   int64_t first_col, void* stream);
 int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* first_error_code, int64_t* first_error_pair);
+/* Several asynchronous *_device / *_peers launches, one collect: after this call (which resets the status on
+ * `stream`) the launches of the context share one error word and counter set until the next
+ * pharmsol_cuda_collect_errors, which reports the first failing pair over all of them (matrix.rs:96-104). */
+int32_t pharmsol_cuda_status_batch_begin(pcu_ctx* ctx, void* stream);
 /* row-major host support points -> SoA device buffer (H2D + on-device transpose) */
 int32_t pharmsol_cuda_upload_support_points(pcu_ctx* ctx, const double* support_points, int64_t nspp, int32_t nparams,
                                             double* spp_soa_dev, int64_t ld_spp, void* stream);

@@ -125,6 +125,7 @@ def lib():
         "pharmsol_cuda_log_likelihood_matrix_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, i64, vp]),
         "pharmsol_cuda_log_likelihood_matrix_peers": (i32, [vp, vp, vp, vp, i64, i64, P(vp), i32, i64, i64, vp]),
         "pharmsol_cuda_collect_errors": (i32, [vp, P(i32), P(i64)]),
+        "pharmsol_cuda_status_batch_begin": (i32, [vp, vp]),
         "pharmsol_cuda_upload_support_points": (i32, [vp, dp, i64, i32, vp, i64, vp]),
         "pharmsol_cuda_predictions": (i32, [vp, vp, vp, dp, i64, i32, dp]),
         "pharmsol_cuda_predictions_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, i64, vp]),
@@ -461,6 +462,11 @@ def upload_support_points(ctx, support_points, spp_soa_ptr, ld_spp, stream=0):
     nspp, npar = spp.shape
     check(lib().pharmsol_cuda_upload_support_points(ctx.ptr, _dp(spp), nspp, npar, C.c_void_p(int(spp_soa_ptr)), int(ld_spp),
                                                     C.c_void_p(int(stream) or None)))
+
+
+def status_batch_begin(ctx, stream=0):
+    """The launches that follow share one error word / counter set until the next collect_errors."""
+    check(lib().pharmsol_cuda_status_batch_begin(ctx.ptr, C.c_void_p(int(stream) or None)))
 
 
 def log_likelihood_matrix_device(ctx, model, pop, spp_soa_ptr, ncols, ld_spp, out_ptr, ld_out, first_col=0, stream=0):

@@ -750,7 +750,7 @@ class ResidentPsi:
     """
 
     def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True,
-                 peer_stores="auto"):
+                 peer_stores="auto", gather_overlap="auto"):
         import torch
         import torch.distributed as dist
         from .sharding import ShardedPsi
@@ -770,14 +770,21 @@ class ResidentPsi:
             # 8 GPUs 42.8 ms fused vs 44.3 ms with NCCL) and lose when psi is produced at GB/s rates (closed forms: C3 on
             # 8 GPUs 63.5 ms fused vs 57.0 ms with the bulk NCCL all-gather)
             peer_stores = equation.kind() != EqnKind.Analytical
-        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=bool(peer_stores)) if (shard and dist.is_available() and dist.is_initialized()) \
+        multi = shard and dist.is_available() and dist.is_initialized()
+        if gather_overlap == "auto":
+            # NCCL path with a big matrix: evaluate 7/8 of this rank's columns, all-gather them while the last 1/8 is
+            # evaluated (sharding.ColumnPartition phases); not worth a second launch for small matrices
+            gather_overlap = (not peer_stores) and multi and self.nsub * self.nspp * 8 >= (256 << 20)
+        self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=bool(peer_stores), tail_fraction=0.125 if gather_overlap else 0.0) if multi \
             else _SingleRank(self.nsub, self.nspp, self.device)
-        lo, hi = self.sharded.local_range
-        self.first_col, self.ncols = lo, hi - lo
+        self.ranges = [r for r in self.sharded.local_ranges]
+        self.first_col = self.ranges[0][0]
+        self.ncols = sum(hi - lo for lo, hi in self.ranges)
+        self.columns = np.concatenate([np.arange(lo, hi) for lo, hi in self.ranges]) if self.ranges else np.zeros(0, dtype=np.int64)
         self.ld_spp = max(self.ncols, 1)
         self.spp_soa = torch.empty((self.nparams, self.ld_spp), dtype=torch.float64, device=self.device)
         if self.ncols:
-            _lib.upload_support_points(self.ctx, spp[lo:hi], self.spp_soa.data_ptr(), self.ld_spp, self._stream())
+            _lib.upload_support_points(self.ctx, spp[self.columns], self.spp_soa.data_ptr(), self.ld_spp, self._stream())
             torch.cuda.current_stream(self.device).synchronize()
         equation._model.compile(self.ctx)
 
@@ -787,23 +794,51 @@ class ResidentPsi:
         h = self.torch.cuda.current_stream(self.device).cuda_stream
         return h if h else 1
 
-    def launch(self):
-        """One asynchronous psi kernel launch for this rank's columns (no copies, no sync)."""
-        if not self.ncols:
+    def _launch_phase(self, p, offset):
+        lo, hi = self.ranges[p]
+        if hi <= lo:
             return
+        spp_ptr = self.spp_soa.data_ptr() + 8 * offset
         peers = getattr(self.sharded, "peer_ptrs", None)
         if peers is not None:      # fused all-gather: results go straight into every rank's full matrix
-            _lib.log_likelihood_matrix_peers(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,
-                                             peers, self.nsub, self.first_col, self._stream())
+            _lib.log_likelihood_matrix_peers(self.ctx, self.eq._model, self.pop, spp_ptr, hi - lo, self.ld_spp, peers, self.nsub, lo, self._stream())
             return
-        slab = self.sharded.local_slab()
-        _lib.log_likelihood_matrix_device(self.ctx, self.eq._model, self.pop, self.spp_soa.data_ptr(), self.ncols, self.ld_spp,
-                                          slab.data_ptr(), self.nsub, self.first_col, self._stream())
+        _lib.log_likelihood_matrix_device(self.ctx, self.eq._model, self.pop, spp_ptr, hi - lo, self.ld_spp,
+                                          self.sharded.local_slab(p).data_ptr(), self.nsub, lo, self._stream())
 
-    def step(self):
-        """launch + all-gather of the column slabs (no-op on one rank); asynchronous."""
-        self.launch()
-        self.sharded.gather()
+    def launch(self):
+        """Asynchronous psi kernel launches for this rank's columns (one per phase; no copies, no sync)."""
+        if not self.ncols:
+            return
+        if len(self.ranges) > 1:
+            _lib.status_batch_begin(self.ctx, self._stream())
+        offset = 0
+        for p, (lo, hi) in enumerate(self.ranges):
+            self._launch_phase(p, offset)
+            offset += hi - lo
+
+    def step(self, after_compute=None):
+        """launch + all-gather of the column slabs (no-op on one rank); asynchronous.  With two phases the all-gather
+        of the first runs (NCCL's own stream) while the second is evaluated.  `after_compute()` is called right after
+        the last kernel launch (bench: an event that brackets the compute part)."""
+        if len(self.ranges) == 1:
+            self.launch()
+            if after_compute:
+                after_compute()
+            self.sharded.gather()
+            return
+        if self.ncols:
+            _lib.status_batch_begin(self.ctx, self._stream())
+        works, offset = [], 0
+        for p, (lo, hi) in enumerate(self.ranges):
+            self._launch_phase(p, offset)
+            offset += hi - lo
+            if p == len(self.ranges) - 1 and after_compute:
+                after_compute()
+            works.append(self.sharded.gather_phase(p, async_op=True))
+        for w in works:
+            if w is not None:
+                w.wait()
 
     def finish(self):
         """Synchronise, raise the first error over all ranks (matrix.rs:96-104), return psi as a
@@ -826,12 +861,16 @@ class _SingleRank:
         self.world, self.rank, self.nsub, self.nspp = 1, 0, nsub, nspp
         self.full = torch.empty((nspp, nsub), dtype=torch.float64, device=device)
         self.local_range = (0, nspp)
+        self.local_ranges = [(0, nspp)]
 
-    def local_slab(self):
+    def local_slab(self, phase=-1):
         return self.full
 
     def gather(self):
         return self.full
+
+    def gather_phase(self, phase, async_op=False):
+        return None
 
     def reduce_error(self, code, pair):
         return code, pair

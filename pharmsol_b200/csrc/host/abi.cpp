@@ -451,12 +451,28 @@ int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_populat
         return (int32_t)PCU_OK;
     });
 }
+int32_t pharmsol_cuda_status_batch_begin(pcu_ctx* ctx, void* stream) {
+    return guarded([&] {
+        if (!ctx) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        Ctx& c = ctx->c;
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        cudaStream_t s = pick_stream(c, stream);
+        c.err_ctr.reserve(5 * sizeof(unsigned long long));
+        cuda_check(cudaMemcpyAsync(c.err_ctr.p, c.err_host + 8, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s), "reset status");
+        cuda_check(cudaEventRecord(c.ev0, s), "event record");
+        c.status_clean_on = nullptr;
+        c.status_batch = true;
+        return (int32_t)PCU_OK;
+    });
+}
 int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* code, int64_t* pair) {
     return guarded([&] {
         if (!ctx) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
         std::lock_guard<std::mutex> lk(ctx->c.mu);
         cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
         cuda_check(cudaDeviceSynchronize(), "synchronize");
+        ctx->c.status_batch = false;
         return collect(ctx->c, code, pair);
     });
 }
@@ -473,6 +489,7 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         std::lock_guard<std::mutex> lk(ctx->c.mu);
         Ctx& c = ctx->c;
         cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        c.status_batch = false;      // a host-buffer call resets and reads the status itself
         const int64_t nsub = pop->p.flat.nsub;
         if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
         c.spp_soa.reserve((size_t)nspp * np * 8);
@@ -561,6 +578,7 @@ int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* po
         std::lock_guard<std::mutex> lk(ctx->c.mu);
         Ctx& c = ctx->c;
         cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        c.status_batch = false;
         const int64_t nobs = pop->p.flat.nobs_total;
         if (nspp == 0 || nobs == 0) return (int32_t)PCU_OK;
         c.spp_rows.reserve((size_t)nspp * np * 8);
@@ -595,6 +613,7 @@ int32_t pharmsol_cuda_log_likelihood_batch(pcu_ctx* ctx, pcu_model* m, pcu_popul
         std::lock_guard<std::mutex> lk(ctx->c.mu);
         Ctx& c = ctx->c;
         cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        c.status_batch = false;
         psi::RunOpts opt = m->m.opts;
         opt.diagonal = 1;
         opt.nresid = n_models;

@@ -52,6 +52,7 @@ struct Ctx {
     DevBuf spp_rows, spp_soa, out, pred, scratch;
     DevBuf col_work, col_idx, col_sort;      // work-balanced column order (ODE): probe counts, permutation, cub scratch
     int64_t launches = 0;
+    bool status_batch = false;                // several launches share one error word / counter set until the next collect
     cudaStream_t status_clean_on = nullptr;   // stream on which a status reset is already queued behind the previous call (latency path)
     double last_kernel_ms = 0.0;
     unsigned long long last_counters[4] = {0, 0, 0, 0};

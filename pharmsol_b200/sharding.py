@@ -19,25 +19,53 @@ import numpy as np
 
 @dataclass(frozen=True)
 class ColumnPartition:
-    """Equal contiguous column blocks; the last block may be partly padding."""
+    """Equal contiguous column blocks; the last block may be partly padding.
+
+    ``tail_fraction`` > 0 splits the columns into two PHASES, each sharded over all ranks: phase 0 = the first
+    ``~(1 - tail_fraction)`` of the columns (a multiple of ``world``, so it has no padding), phase 1 = the rest.  Every
+    phase is one contiguous block of the full matrix and every rank's share of it one contiguous slab inside that block, so
+    the all-gather of a phase stays in place and can run while the next phase is computed (closed-form models, whose
+    all-gather is not negligible next to the kernel)."""
     nspp: int
     world: int
+    tail_fraction: float = 0.0
+
+    def phase_list(self):
+        """[(first column, columns, shard)] per phase."""
+        w = max(self.world, 1)
+        head = 0
+        if self.tail_fraction > 0.0 and self.world > 1:
+            head = int(self.nspp * (1.0 - self.tail_fraction)) // w * w
+            if head <= 0 or head >= self.nspp:
+                head = 0
+        out = []
+        if head:
+            out.append((0, head, head // w))
+        rest = self.nspp - head
+        out.append((head, rest, (rest + w - 1) // w if self.world > 0 else 0))
+        return out
 
     @property
     def shard(self) -> int:
-        return (self.nspp + self.world - 1) // self.world if self.world > 0 else 0
+        """Columns per rank (single phase) / in the last phase."""
+        return self.phase_list()[-1][2]
 
     @property
     def padded(self) -> int:
-        return self.shard * self.world
+        start, _, shard = self.phase_list()[-1]
+        return start + shard * self.world
 
-    def range(self, rank: int):
-        lo = min(rank * self.shard, self.nspp)
-        hi = min(lo + self.shard, self.nspp)
+    def range(self, rank: int, phase: int = -1):
+        start, count, shard = self.phase_list()[phase]
+        lo = min(start + rank * shard, start + count)
+        hi = min(lo + shard, start + count)
         return lo, hi
 
+    def ranges(self, rank: int):
+        return [self.range(rank, p) for p in range(len(self.phase_list()))]
+
     def counts(self):
-        return [self.range(r)[1] - self.range(r)[0] for r in range(self.world)]
+        return [sum(hi - lo for lo, hi in self.ranges(r)) for r in range(self.world)]
 
 
 def pack_error(code: int, pair: int) -> int:
@@ -60,14 +88,15 @@ class ShardedPsi:
     and return ``(error_code, first_failing_global_pair)``.
     """
 
-    def __init__(self, nsub: int, nspp: int, device, dtype=None, group=None, peer_stores=False):
+    def __init__(self, nsub: int, nspp: int, device, dtype=None, group=None, peer_stores=False, tail_fraction=0.0):
         import torch
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.part = ColumnPartition(int(nspp), self.world)
+        # the fused path has no collective to overlap: phases only make sense for the NCCL / gloo all-gather
+        self.part = ColumnPartition(int(nspp), self.world, 0.0 if peer_stores else float(tail_fraction))
         self.nsub, self.nspp = int(nsub), int(nspp)
         self.device = device
         # column-major psi == C-order (columns, nsub); padded to world * shard columns
@@ -91,12 +120,28 @@ class ShardedPsi:
 
     @property
     def local_range(self):
+        """(lo, hi) of this rank's columns when there is one phase (the common case)."""
         return self.part.range(self.rank)
 
-    def local_slab(self):
-        """This rank's block of columns as a view into the full matrix (shard x nsub, padding included)."""
-        s = self.part.shard
-        return self.full[self.rank * s:(self.rank + 1) * s]
+    @property
+    def local_ranges(self):
+        return self.part.ranges(self.rank)
+
+    @property
+    def nphases(self):
+        return len(self.part.phase_list())
+
+    def local_slab(self, phase: int = -1):
+        """This rank's block of columns of one phase as a view into the full matrix (shard x nsub, padding included)."""
+        start, _, s = self.part.phase_list()[phase]
+        return self.full[start + self.rank * s:start + (self.rank + 1) * s]
+
+    def gather_phase(self, phase: int, async_op: bool = False):
+        """In-place all-gather of one phase's slabs; returns the work handle when asynchronous."""
+        if self.world <= 1 or self.peer_ptrs is not None:
+            return None
+        start, _, s = self.part.phase_list()[phase]
+        return self.dist.all_gather_into_tensor(self.full[start:start + s * self.world], self.local_slab(phase), group=self.group, async_op=async_op)
 
     def gather(self):
         """In-place all-gather of the slabs (each rank's input IS its slice of the output); with peer stores the
@@ -105,7 +150,8 @@ class ShardedPsi:
             if self.peer_ptrs is not None:
                 self.symm.barrier()
             else:
-                self.dist.all_gather_into_tensor(self.full, self.local_slab(), group=self.group)
+                for p in range(self.nphases):
+                    self.gather_phase(p)
         return self.full
 
     def reduce_error(self, code: int, pair: int):
@@ -116,11 +162,20 @@ class ShardedPsi:
         return unpack_error(int(self._err.item()))
 
     def run(self, evaluate):
-        lo, hi = self.local_range
-        slab = self.local_slab()
-        code, pair = evaluate(lo, hi - lo, slab[: hi - lo]) if hi > lo else (0, -1)
-        self.gather()
-        return self.reduce_error(code, pair)
+        """Evaluate phase after phase; the all-gather of a phase runs while the next phase is evaluated."""
+        works, first = [], (0, -1)
+        for p, (lo, hi) in enumerate(self.local_ranges):
+            code, pair = evaluate(lo, hi - lo, self.local_slab(p)[: hi - lo]) if hi > lo else (0, -1)
+            if code and (first[0] == 0 or pair < first[1]):
+                first = (code, pair)
+            if self.peer_ptrs is None:
+                works.append(self.gather_phase(p, async_op=True))
+        if self.peer_ptrs is not None:
+            self.gather()
+        for w in works:
+            if w is not None:
+                w.wait()
+        return self.reduce_error(*first)
 
     def matrix(self):
         """(nsub, nspp) F-order view semantics: returns the (nspp, nsub) C-order tensor transposed."""

@@ -27,34 +27,36 @@ for name, nsub, nspp, kw in [("c1", 40, 1003, {}), ("c2", 64, 2500, dict(solver=
     if "particles" in kw:      # SDE streams are keyed by the global pair index: sharding must not change psi
         eq.with_particles(kw["particles"]).with_mode(ps.SdeMode.ParticleFilter).with_seed(99)
     ref = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)          # whole matrix on this GPU, host API
-    for peer in (True, False):
-        job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=peer)
+    # fused peer stores | one NCCL all-gather | phased: 7/8 of the columns gathered while the last 1/8 computes
+    for peer, overlap in ((True, False), (False, False), (False, True)):
+        job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=peer, gather_overlap=overlap)
         fused = getattr(job.sharded, "peer_ptrs", None) is not None
-        job.step()
+        for _ in range(2):      # twice: the second step runs over the first one's status / buffers
+            job.step()
         psi = job.finish().cpu().numpy()
         same = np.array_equal(psi, ref, equal_nan=True)
-        ok = ok and same and (fused == peer)
-        print(f"rank {rank} {name} peer_stores={peer} fused={fused} equal_to_single_gpu={same} err={getattr(job.sharded, 'peer_error', None)}", flush=True)
+        ok = ok and same and (fused == peer) and (len(job.ranges) == (2 if overlap else 1))
+        print(f"rank {rank} {name} peer_stores={peer} overlap={overlap} fused={fused} equal_to_single_gpu={same} err={getattr(job.sharded, 'peer_error', None)}", flush=True)
         dist.barrier()
 # first error propagates to every rank with its global pair index
 eq = ps.Equation.from_dsl("name = twocpt\nkind = analytical\nparams = ke, kcp, kpc, v\nstates = central, peripheral\noutputs = cp\nbolus(iv) -> central\n"
                           "structure = two_compartments\nout(cp) = central / v ~ continuous()\n")
 ops = [("bolus", 0.0, 100.0, "iv"), ("observation", 1.0, 50.0, "cp")]
 data = ps.Data([ps.Subject(f"s{i}", ops) for i in range(5)])
-spp = np.tile(np.array([[0.1, 3.0, 1.0, 1.0]]), (400, 1))
-spp[333] = [1.0, -3.0, 1.5, 1.0]
 ems = ps.AssayErrorModels().add("cp", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0))
-for peer in (True, False):
-    job = ps.ResidentPsi(eq, data, spp, ems, device=dev, peer_stores=peer)
+for peer, overlap, bad in ((True, False, 333), (False, False, 333), (False, True, 390), (False, True, 20)):
+    spp = np.tile(np.array([[0.1, 3.0, 1.0, 1.0]]), (400, 1))
+    spp[bad] = [1.0, -3.0, 1.5, 1.0]      # with two phases column 390 falls in the tail phase, column 20 in the head phase
+    job = ps.ResidentPsi(eq, data, spp, ems, device=dev, peer_stores=peer, gather_overlap=overlap)
     job.step()
     try:
         job.finish()
         ok = False
         print(f"rank {rank}: expected an error", flush=True)
     except ps.PharmsolError as e:
-        good = e.code == 12 and e.pair == 0 + 333 * 5
+        good = e.code == 12 and e.pair == 0 + bad * 5
         ok = ok and good
-        print(f"rank {rank} error propagation peer_stores={peer}: code {e.code} pair {e.pair} ok={good}", flush=True)
+        print(f"rank {rank} error propagation peer_stores={peer} overlap={overlap}: code {e.code} pair {e.pair} ok={good}", flush=True)
     dist.barrier()
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -24,6 +24,27 @@ def test_partition_covers_all_columns():
             assert sum(p.counts()) == nspp and p.padded >= nspp and p.padded - nspp < max(world, 1)
 
 
+def test_phased_partition_keeps_every_phase_contiguous_and_in_place():
+    """Two phases (7/8 + 1/8 of the columns, each sharded over all ranks): every column has exactly one owner, the head
+    phase has no padding, and each rank's share of a phase is one contiguous slab inside the phase's block."""
+    for nspp in (0, 1, 7, 64, 1001, 50000):
+        for world in (1, 2, 3, 8):
+            for tail in (0.125, 0.5):
+                p = ColumnPartition(nspp, world, tail)
+                phases = p.phase_list()
+                assert 1 <= len(phases) <= 2 and phases[0][0] == 0 and sum(c for _, c, _ in phases) == nspp
+                if len(phases) == 2:
+                    assert phases[0][1] % world == 0 and phases[0][1] == phases[0][2] * world and phases[1][0] == phases[0][1]
+                owner = np.full(nspp, -1)
+                for r in range(world):
+                    for ph, (lo, hi) in enumerate(p.ranges(r)):
+                        assert np.all(owner[lo:hi] == -1)
+                        owner[lo:hi] = r
+                        start, count, shard = phases[ph]
+                        assert lo == min(start + r * shard, start + count)
+                assert np.all(owner >= 0) and sum(p.counts()) == nspp and nspp <= p.padded < nspp + max(world, 1)
+
+
 def test_error_word_orders_by_pair_then_code():
     assert unpack_error(pack_error(0, 5)) == (0, -1)
     assert unpack_error(pack_error(7, 123456789012)) == (7, 123456789012)
@@ -44,11 +65,12 @@ def _truth(nsub, nspp):
     return -(i * 1000.0 + j) - 0.25
 
 
-def _worker(rank, world, port, nsub, nspp, fail_at, out):
+def _worker(rank, world, port, nsub, nspp, fail_at, out, tail=0.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        sp = ShardedPsi(nsub, nspp, torch.device("cpu"))
+        sp = ShardedPsi(nsub, nspp, torch.device("cpu"), tail_fraction=tail)
+        assert sp.nphases == len(ColumnPartition(nspp, world, tail).phase_list()) == (2 if tail else 1)
         truth = torch.from_numpy(_truth(nsub, nspp))
 
         def evaluate(first_col, ncols, slab):
@@ -66,12 +88,14 @@ def _worker(rank, world, port, nsub, nspp, fail_at, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nspp,fail_at", [(2, 10, None), (2, 11, (3, 7)), (3, 8, (0, 2))])
-def test_sharded_assembly_gloo(world, nspp, fail_at):
+@pytest.mark.parametrize("world,nspp,fail_at,tail", [(2, 10, None, 0.0), (2, 11, (3, 7), 0.0), (3, 8, (0, 2), 0.0),
+                                                     (2, 37, None, 0.125), (2, 37, (1, 35), 0.125), (3, 100, (4, 5), 0.25)])
+def test_sharded_assembly_gloo(world, nspp, fail_at, tail):
+    """tail > 0: two phases, the all-gather of the first is asynchronous and overlaps the evaluation of the second."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 5, nspp, fail_at, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 5, nspp, fail_at, q, tail)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
