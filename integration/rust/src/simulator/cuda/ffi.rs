@@ -64,6 +64,7 @@ extern "C" {
     pub fn pharmsol_cuda_log_likelihood_matrix_device(ctx: *mut pcu_ctx, m: *mut pcu_model, pop: *mut pcu_population,
         spp_soa_dev: *const f64, ncols: i64, ld_spp: i64, out_dev: *mut f64, ld_out: i64, first_col: i64, stream: *mut c_void) -> i32;
     pub fn pharmsol_cuda_collect_errors(ctx: *mut pcu_ctx, code: *mut i32, pair: *mut i64) -> i32;
+    pub fn pharmsol_cuda_status_batch_begin(ctx: *mut pcu_ctx, stream: *mut c_void) -> i32;
     // fused all-gather: results stored straight into every rank's full psi through peer-mapped pointers
     pub fn pharmsol_cuda_log_likelihood_matrix_peers(ctx: *mut pcu_ctx, m: *mut pcu_model, pop: *mut pcu_population,
         spp_soa_dev: *const f64, ncols: i64, ld_spp: i64, out_full_peers: *const *mut f64, npeers: i32, ld_out: i64, first_col: i64,

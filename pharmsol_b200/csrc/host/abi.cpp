@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 
 #include "../../../include/pharmsol_cuda.h"
 #include "runtime.hpp"
@@ -97,7 +98,7 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
         cudaDeviceProp prop;
         cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
         if (prop.major < 10) throw CudaError(std::string("device `") + prop.name + "` is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this backend is built for sm_100a only");
-        auto* c = new pcu_ctx();
+        std::unique_ptr<pcu_ctx> c(new pcu_ctx());      // ~Ctx releases whatever was created if a later step throws
         c->c.device = device;
         c->c.sm_count = prop.multiProcessorCount;
         cuda_check(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -110,7 +111,7 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
         std::memset(c->c.err_host, 0, 16 * sizeof(unsigned long long));
         c->c.err_host[8] = ~0ull;
         cuda_check(cudaMallocHost((void**)&c->c.small_host, Ctx::kSmallIn + Ctx::kSmallOut), "cudaMallocHost");
-        *out = c;
+        *out = c.release();
         return (int32_t)PCU_OK;
     });
 }
@@ -208,10 +209,8 @@ int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap) {
 
 // ---- models ----------------------------------------------------------------------------------------------
 static pcu_model* make_model(const std::string& source) {
-    auto* m = new pcu_model();
-    try {
-        m->m.cm = dsl::compile_source(source);
-    } catch (...) { delete m; throw; }
+    std::unique_ptr<pcu_model> m(new pcu_model());
+    m->m.cm = dsl::compile_source(source);
     m->m.dsl_source = source;
     std::memset(&m->m.opts, 0, sizeof m->m.opts);
     m->m.opts.rtol = 1e-4; m->m.opts.atol = 1e-4;            // ode/mod.rs:40-41
@@ -230,7 +229,7 @@ static pcu_model* make_model(const std::string& source) {
     if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 5; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
     else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
     m->m.source_cache = m->m.cm.cuda_source(entries, false);
-    return m;
+    return m.release();
 }
 int32_t pharmsol_cuda_model_from_dsl(pcu_ctx*, const char* source, size_t len, pcu_model** out) {
     return guarded([&] {
@@ -258,14 +257,14 @@ int32_t pharmsol_cuda_model_load_artifact(pcu_ctx*, const char* path, pcu_model*
     return guarded([&] {
         if (!path || !out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
         ArtifactFile a = read_artifact(path);
-        pcu_model* m = make_model(a.dsl_source);
+        std::unique_ptr<pcu_model> m(make_model(a.dsl_source));
         try {
             apply_artifact_settings(a.settings, m->m.opts);
-        } catch (const std::exception&) { delete m; throw PharmsolError(PCU_ERR_OTHER, std::string("artifact ") + path + " has malformed settings"); }
+        } catch (const std::exception&) { throw PharmsolError(PCU_ERR_OTHER, std::string("artifact ") + path + " has malformed settings"); }
         // Device code compiled against another engine build (other kernel-parameter layout) is not trusted: the
         // model then takes the usual registry / cache / NVRTC route from the DSL source it carries.
         if (a.engine_matches) m->m.artifact_cubins = std::move(a.cubins);
-        *out = m;
+        *out = m.release();
         return (int32_t)PCU_OK;
     });
 }
