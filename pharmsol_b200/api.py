@@ -772,9 +772,12 @@ class ResidentPsi:
             peer_stores = equation.kind() != EqnKind.Analytical
         multi = shard and dist.is_available() and dist.is_initialized()
         if gather_overlap == "auto":
-            # NCCL path with a big matrix: evaluate 7/8 of this rank's columns, all-gather them while the last 1/8 is
-            # evaluated (sharding.ColumnPartition phases); not worth a second launch for small matrices
-            gather_overlap = (not peer_stores) and multi and self.nsub * self.nspp * 8 >= (256 << 20)
+            # Phased gather (evaluate 7/8 of this rank's columns, all-gather them while the last 1/8 is evaluated;
+            # sharding.ColumnPartition phases) is opt-in: on 8 GPUs C3 measured 38.3 ms phased vs 37.8 ms with one bulk
+            # all-gather — at default stream priority NCCL's kernel waits behind the queued CTAs of the tail phase
+            # (profiles/r01_tuning.md)
+            gather_overlap = False
+        gather_overlap = bool(gather_overlap) and (not peer_stores) and multi
         self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=bool(peer_stores), tail_fraction=0.125 if gather_overlap else 0.0) if multi \
             else _SingleRank(self.nsub, self.nspp, self.device)
         self.ranges = [r for r in self.sharded.local_ranges]
