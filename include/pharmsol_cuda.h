@@ -125,7 +125,9 @@ void pharmsol_subject_builder_observation_with_error(pcu_subject_builder* b, dou
 void pharmsol_subject_builder_covariate(pcu_subject_builder* b, const char* name, double time, double value);
 void pharmsol_subject_builder_repeat(pcu_subject_builder* b, int64_t n, double delta);
 void pharmsol_subject_builder_reset(pcu_subject_builder* b);            /* next occasion */
-pcu_subject* pharmsol_subject_builder_build(pcu_subject_builder* b);    /* consumes the builder */
+/* consumes the builder; NULL (message in pharmsol_cuda_last_error_message) if any builder call before it failed:
+ * NULL label, censoring outside 0..2, repeat count outside [0, 10^7], out of memory */
+pcu_subject* pharmsol_subject_builder_build(pcu_subject_builder* b);
 /* Covariate::set_fixed (data/covariate.rs:243-248): carry-forward instead of linear interpolation */
 int32_t pharmsol_subject_set_covariate_fixed(pcu_subject* s, int32_t occasion, const char* name, int32_t fixed);
 void pharmsol_subject_free(pcu_subject* s);

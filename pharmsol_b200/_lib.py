@@ -262,6 +262,8 @@ class NativeSubject:
             else:
                 raise ValueError(f"unknown subject op {op!r}")
         self.ptr = C.c_void_p(L.pharmsol_subject_builder_build(b))
+        if not self.ptr:
+            raise PharmsolError(66, _msg())
         for op in fixed:
             check(L.pharmsol_subject_set_covariate_fixed(self.ptr, int(op[1]), _b(op[2]), int(bool(op[3]))))
 

@@ -12,7 +12,7 @@ using namespace pharmsol;
 
 struct pcu_ctx { Ctx c; };
 struct pcu_model { Model m; };
-struct pcu_subject_builder { SubjectBuilder b; explicit pcu_subject_builder(const char* id) : b(id) {} };
+struct pcu_subject_builder { SubjectBuilder b; std::string error; explicit pcu_subject_builder(const char* id) : b(id) {} };
 struct pcu_subject { Subject s; };
 struct pcu_data { Data d; };
 struct pcu_population { Population p; AssayErrorModels em; bool has_em = false; };
@@ -76,6 +76,22 @@ int32_t collect(Ctx& c, int32_t* code, int64_t* pair, bool prefetched = false) {
     return ec;
 }
 
+// The builder entry points return nothing (they mirror the reference's chained builder), so a failure — a NULL label,
+// an absurd repeat count, out of memory — is remembered in the builder and reported by ..._build(), which then returns
+// NULL with the message in pharmsol_cuda_last_error_message.  Nothing may unwind through the C boundary.
+template <class F>
+static void builder_op(pcu_subject_builder* b, F&& f) {
+    if (!b) { set_last_error("NULL subject builder"); return; }
+    if (!b->error.empty()) return;
+    try { f(); }
+    catch (const std::exception& e) { b->error = e.what(); }
+    catch (...) { b->error = "unknown error in the subject builder"; }
+}
+static const char* label_or_throw(const char* s, const char* what) {
+    if (!s) throw PharmsolError(PCU_ERR_INVALID_ARGUMENT, std::string("NULL ") + what + " label");
+    return s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -132,28 +148,53 @@ int32_t pharmsol_cuda_host_free(void* p) {
 }
 
 // ---- data ------------------------------------------------------------------------------------------------
-pcu_subject_builder* pharmsol_subject_builder_new(const char* id) { return new pcu_subject_builder(id ? id : ""); }
-void pharmsol_subject_builder_bolus(pcu_subject_builder* b, double t, double a, const char* input) { b->b.bolus(t, a, input); }
-void pharmsol_subject_builder_infusion(pcu_subject_builder* b, double t, double a, const char* input, double dur) { b->b.infusion(t, a, input, dur); }
-void pharmsol_subject_builder_observation(pcu_subject_builder* b, double t, double v, const char* outeq) { b->b.observation(t, v, outeq); }
-void pharmsol_subject_builder_censored_observation(pcu_subject_builder* b, double t, double v, const char* outeq, int32_t cens) {
-    b->b.censored_observation(t, v, outeq, (Censor)cens);
+pcu_subject_builder* pharmsol_subject_builder_new(const char* id) {
+    try { return new pcu_subject_builder(id ? id : ""); } catch (const std::exception& e) { set_last_error(e.what()); return nullptr; }
 }
-void pharmsol_subject_builder_missing_observation(pcu_subject_builder* b, double t, const char* outeq) { b->b.missing_observation(t, outeq); }
+void pharmsol_subject_builder_bolus(pcu_subject_builder* b, double t, double a, const char* input) {
+    builder_op(b, [&] { b->b.bolus(t, a, label_or_throw(input, "input")); });
+}
+void pharmsol_subject_builder_infusion(pcu_subject_builder* b, double t, double a, const char* input, double dur) {
+    builder_op(b, [&] { b->b.infusion(t, a, label_or_throw(input, "input"), dur); });
+}
+void pharmsol_subject_builder_observation(pcu_subject_builder* b, double t, double v, const char* outeq) {
+    builder_op(b, [&] { b->b.observation(t, v, label_or_throw(outeq, "output")); });
+}
+void pharmsol_subject_builder_censored_observation(pcu_subject_builder* b, double t, double v, const char* outeq, int32_t cens) {
+    builder_op(b, [&] {
+        if (cens < 0 || cens > 2) throw PharmsolError(PCU_ERR_INVALID_ARGUMENT, "censoring must be 0 (none), 1 (BLOQ) or 2 (ALOQ)");
+        b->b.censored_observation(t, v, label_or_throw(outeq, "output"), (Censor)cens);
+    });
+}
+void pharmsol_subject_builder_missing_observation(pcu_subject_builder* b, double t, const char* outeq) {
+    builder_op(b, [&] { b->b.missing_observation(t, label_or_throw(outeq, "output")); });
+}
 void pharmsol_subject_builder_observation_with_error(pcu_subject_builder* b, double t, double v, const char* outeq, double c0, double c1,
                                                      double c2, double c3, int32_t cens) {
-    b->b.observation_with_error(t, v, outeq, ErrorPoly{c0, c1, c2, c3}, (Censor)cens);
+    builder_op(b, [&] {
+        if (cens < 0 || cens > 2) throw PharmsolError(PCU_ERR_INVALID_ARGUMENT, "censoring must be 0 (none), 1 (BLOQ) or 2 (ALOQ)");
+        b->b.observation_with_error(t, v, label_or_throw(outeq, "output"), ErrorPoly{c0, c1, c2, c3}, (Censor)cens);
+    });
 }
-void pharmsol_subject_builder_covariate(pcu_subject_builder* b, const char* name, double t, double v) { b->b.covariate(name, t, v); }
-void pharmsol_subject_builder_repeat(pcu_subject_builder* b, int64_t n, double delta) { b->b.repeat((size_t)n, delta); }
-void pharmsol_subject_builder_reset(pcu_subject_builder* b) { b->b.reset(); }
+void pharmsol_subject_builder_covariate(pcu_subject_builder* b, const char* name, double t, double v) {
+    builder_op(b, [&] { b->b.covariate(label_or_throw(name, "covariate"), t, v); });
+}
+void pharmsol_subject_builder_repeat(pcu_subject_builder* b, int64_t n, double delta) {
+    builder_op(b, [&] {
+        if (n < 0 || n > 10000000) throw PharmsolError(PCU_ERR_INVALID_ARGUMENT, "repeat count " + std::to_string(n) + " is outside [0, 10000000]");
+        b->b.repeat((size_t)n, delta);
+    });
+}
+void pharmsol_subject_builder_reset(pcu_subject_builder* b) { builder_op(b, [&] { b->b.reset(); }); }
 pcu_subject* pharmsol_subject_builder_build(pcu_subject_builder* b) {
-    auto* s = new pcu_subject{b->b.build()};
-    delete b;
-    return s;
+    if (!b) { set_last_error("NULL subject builder"); return nullptr; }
+    std::unique_ptr<pcu_subject_builder> owned(b);      // consumed either way
+    if (!b->error.empty()) { set_last_error("subject `" + b->b.id + "`: " + b->error); return nullptr; }
+    try { return new pcu_subject{b->b.build()}; }
+    catch (const std::exception& e) { set_last_error(e.what()); return nullptr; }
 }
 int32_t pharmsol_subject_set_covariate_fixed(pcu_subject* s, int32_t occasion, const char* name, int32_t fixed) {
-    if (!s || occasion < 0 || (size_t)occasion >= s->s.occasions.size()) return PCU_ERR_INVALID_ARGUMENT;
+    if (!s || !name || occasion < 0 || (size_t)occasion >= s->s.occasions.size()) return PCU_ERR_INVALID_ARGUMENT;
     auto& covs = s->s.occasions[(size_t)occasion].covariates;
     auto it = covs.find(name);
     if (it == covs.end()) return PCU_ERR_MISSING_COVARIATE;
@@ -161,11 +202,15 @@ int32_t pharmsol_subject_set_covariate_fixed(pcu_subject* s, int32_t occasion, c
     return PCU_OK;
 }
 void pharmsol_subject_free(pcu_subject* s) { delete s; }
-pcu_data* pharmsol_data_new(void) { return new pcu_data(); }
+pcu_data* pharmsol_data_new(void) {
+    try { return new pcu_data(); } catch (const std::exception& e) { set_last_error(e.what()); return nullptr; }
+}
 int32_t pharmsol_data_add_subject(pcu_data* d, const pcu_subject* s) {
-    if (!d || !s) return PCU_ERR_INVALID_ARGUMENT;
-    d->d.subjects.push_back(s->s);
-    return PCU_OK;
+    return guarded([&] {
+        if (!d || !s) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        d->d.subjects.push_back(s->s);
+        return (int32_t)PCU_OK;
+    });
 }
 int64_t pharmsol_data_len(const pcu_data* d) { return d ? (int64_t)d->d.subjects.size() : 0; }
 void pharmsol_data_free(pcu_data* d) { delete d; }
@@ -198,7 +243,8 @@ int32_t pharmsol_data_expand(const pcu_data* d, double idelta, double tad, pcu_d
 }
 int64_t pharmsol_data_describe_json(const pcu_data* d, char* buf, size_t cap) {
     if (!d) return -1;
-    const std::string s = describe_data_json(d->d);
+    std::string s;
+    try { s = describe_data_json(d->d); } catch (const std::exception& e) { set_last_error(e.what()); return -1; }
     if (buf && cap > 0) {
         const size_t n = std::min(cap - 1, s.size());
         std::memcpy(buf, s.data(), n);
@@ -287,13 +333,13 @@ int64_t pharmsol_cuda_artifact_info_json(const char* path, char* buf, size_t cap
     return need;
 }
 void pharmsol_cuda_model_destroy(pcu_model* m) { delete m; }
-int32_t pharmsol_cuda_model_kind(const pcu_model* m) { return (int32_t)m->m.cm.kind; }
-int32_t pharmsol_cuda_model_nparams(const pcu_model* m) { return (int32_t)m->m.cm.parameters.size(); }
-int32_t pharmsol_cuda_model_nstates(const pcu_model* m) { return m->m.cm.state_len; }
-int32_t pharmsol_cuda_model_nouteqs(const pcu_model* m) { return m->m.cm.output_len; }
-const char* pharmsol_cuda_model_info_json(const pcu_model* m) { return m->m.info_json.c_str(); }
-const char* pharmsol_cuda_model_cuda_source(const pcu_model* m) { return m->m.source_cache.c_str(); }
-const char* pharmsol_cuda_model_id(const pcu_model* m) { return m->m.cm.id.c_str(); }
+int32_t pharmsol_cuda_model_kind(const pcu_model* m) { return m ? (int32_t)m->m.cm.kind : -1; }
+int32_t pharmsol_cuda_model_nparams(const pcu_model* m) { return m ? (int32_t)m->m.cm.parameters.size() : -1; }
+int32_t pharmsol_cuda_model_nstates(const pcu_model* m) { return m ? m->m.cm.state_len : -1; }
+int32_t pharmsol_cuda_model_nouteqs(const pcu_model* m) { return m ? m->m.cm.output_len : -1; }
+const char* pharmsol_cuda_model_info_json(const pcu_model* m) { return m ? m->m.info_json.c_str() : ""; }
+const char* pharmsol_cuda_model_cuda_source(const pcu_model* m) { return m ? m->m.source_cache.c_str() : ""; }
+const char* pharmsol_cuda_model_id(const pcu_model* m) { return m ? m->m.cm.id.c_str() : ""; }
 int32_t pharmsol_cuda_model_set_solver(pcu_model* m, int32_t solver, double rtol, double atol) {
     if (!m || solver < 0 || solver > 4 || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
     m->m.opts.solver = solver; m->m.opts.rtol = rtol; m->m.opts.atol = atol;

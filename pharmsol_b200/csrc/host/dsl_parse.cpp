@@ -115,9 +115,22 @@ struct Parser {
         if (op == "^") return 7;
         return 0;
     }
+    // Recursion guard: a shared library must answer degenerate input ("((((...", 10^5 chained operators) with an error,
+    // not with a stack overflow of the host process.  Every recursive production passes through here; chained
+    // left-associative operators are bounded by the number of nodes on the spine (the emitter recurses over it).
+    static constexpr int kMaxDepth = 400;
+    int depth = 0;
+    struct DepthGuard {
+        Parser& p;
+        explicit DepthGuard(Parser& pp) : p(pp) { if (++p.depth > kMaxDepth) throw DslError("expression or block nesting is too deep (limit " + std::to_string(kMaxDepth) + ")", p.peek().pos); }
+        ~DepthGuard() { --p.depth; }
+    };
     ExprP parse_expr(int min_prec = 1) {
+        DepthGuard guard(*this);
         ExprP lhs = parse_unary();
+        int spine = 0;
         while (peek().kind == Tk::Punct) {
+            if (++spine > 4 * kMaxDepth) throw DslError("expression has too many chained operators (limit " + std::to_string(4 * kMaxDepth) + ")", peek().pos);
             const std::string op = peek().text;
             const int p = prec(op);
             if (p == 0 || p < min_prec) break;
@@ -131,6 +144,7 @@ struct Parser {
     }
     // unary + - ! bind tighter than any binary operator (so -a^2 == (-a)^2)
     ExprP parse_unary() {
+        DepthGuard guard(*this);
         if (peek().kind == Tk::Punct && (peek().text == "-" || peek().text == "+" || peek().text == "!")) {
             Token t = bump();
             ExprP u = mk(Expr::Unary, t.pos);
@@ -140,6 +154,7 @@ struct Parser {
         return parse_primary();
     }
     ExprP parse_if_expr() {
+        DepthGuard guard(*this);
         const int pos = bump().pos;   // `if`
         ExprP c = parse_expr();
         ExprP a, b;
@@ -228,6 +243,7 @@ struct Parser {
         return out;
     }
     Stmt parse_stmt() {
+        DepthGuard guard(*this);
         Stmt s;
         s.pos = peek().pos;
         if (at_ident("if")) {

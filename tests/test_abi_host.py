@@ -54,6 +54,38 @@ def test_compute_fails_loudly_without_device(ps):
     assert e.value.code == 64
 
 
+def test_bad_arguments_become_errors_not_crashes(ps):
+    """Nothing may unwind (or overflow the stack) through the C boundary: NULL labels, absurd repeat counts, NULL
+    handles and degenerate DSL sources come back as status codes / NULL + a message."""
+    from pharmsol_b200 import _lib
+    L = _lib.lib()
+    for poison in (lambda b: L.pharmsol_subject_builder_bolus(b, 0.0, 1.0, None),
+                   lambda b: L.pharmsol_subject_builder_observation(b, 0.0, 1.0, None),
+                   lambda b: L.pharmsol_subject_builder_covariate(b, None, 0.0, 1.0),
+                   lambda b: (L.pharmsol_subject_builder_bolus(b, 0.0, 1.0, b"iv"), L.pharmsol_subject_builder_repeat(b, -1, 1.0)),
+                   lambda b: (L.pharmsol_subject_builder_bolus(b, 0.0, 1.0, b"iv"), L.pharmsol_subject_builder_repeat(b, 10**12, 1.0)),
+                   lambda b: L.pharmsol_subject_builder_censored_observation(b, 0.0, 1.0, b"cp", 9)):
+        b = L.pharmsol_subject_builder_new(b"bad")
+        poison(b)
+        L.pharmsol_subject_builder_bolus(b, 1.0, 1.0, b"iv")        # later calls on a poisoned builder are ignored
+        assert L.pharmsol_subject_builder_build(b) is None
+        assert b"subject `bad`" in L.pharmsol_cuda_last_error_message()
+    L.pharmsol_subject_builder_bolus(None, 0.0, 1.0, b"iv")
+    assert L.pharmsol_subject_builder_build(None) is None
+    with pytest.raises(ps.PharmsolError, match="repeat count -3"):
+        _lib.NativeSubject("s", [("bolus", 0.0, 1.0, "iv"), ("repeat", -3, 1.0)])
+    assert L.pharmsol_cuda_model_kind(None) == -1 and L.pharmsol_cuda_model_nparams(None) == -1
+    assert L.pharmsol_cuda_model_info_json(None) == b"" and L.pharmsol_cuda_model_id(None) == b""
+    assert L.pharmsol_data_add_subject(None, None) == 66 and L.pharmsol_data_len(None) == 0
+    # degenerate sources: deep nesting and endless operator chains are compile errors, not stack overflows
+    base = "name = d\nkind = ode\nparams = ke\nstates = c\noutputs = y\ndx(c) = -ke * c\nout(y) = %s ~ continuous()\n"
+    for expr in ("(" * 50000 + "c" + ")" * 50000, "-" * 50000 + "c", "c" + " + c" * 50000, "c" + " ^ c" * 50000,
+                 "if (c > 0) { " * 5000 + "1" + " } else { 2 }" * 5000):
+        with pytest.raises(ps.PharmsolError, match="too deep|too many chained"):
+            ps.Equation.from_dsl(base % expr)
+    assert ps.Equation.from_dsl(base % ("c" + " + c" * 1000)).nstates() == 1
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under pharmsol_b200/ may reference it."""
     pkg = os.path.join(ROOT, "pharmsol_b200")
