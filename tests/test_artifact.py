@@ -91,6 +91,23 @@ def test_bad_artifacts_are_rejected(ps, tmp_path):
         ps.load_aot_model(tmp_path / "v2.pkm")
 
 
+def test_unknown_sections_are_skipped(ps, tmp_path):
+    """Forward compatibility inside one API version: a reader ignores section tags it does not know."""
+    path = ps.Equation.from_dsl(ANA_SRC).export_artifact(tmp_path / "a.pkm")
+    raw = open(path, "rb").read()
+    body = bytearray(raw[:-8])
+    struct.pack_into("<I", body, 12, struct.unpack_from("<I", body, 12)[0] + 1)
+    extra = b"future section payload"
+    body += struct.pack("<IIQ", 99, 7, len(extra)) + extra
+    h = 1469598103934665603
+    for b in body:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    (tmp_path / "future.pkm").write_bytes(bytes(body) + struct.pack("<Q", h))
+    info = ps.read_aot_model_info(tmp_path / "future.pkm")
+    assert info["model"]["name"] == "artifact_ana" and len(info["kernels"]) == 1
+    assert ps.load_aot_model(tmp_path / "future.pkm").parameter_names() == ["ka", "ke", "v"]
+
+
 def test_foreign_engine_cubin_is_not_trusted(ps, tmp_path, monkeypatch):
     """An artifact built by another engine build keeps working through its DSL source; its device code is dropped."""
     path = ps.Equation.from_dsl(ANA_SRC).export_artifact(tmp_path / "a.pkm")
