@@ -111,7 +111,9 @@ struct CompiledModel {
 };
 
 CompiledModel compile_model(const ModelAst& ast);
-inline CompiledModel compile_source(const std::string& src) { return compile_model(parse_model(src)); }
+// parse + analyse + emit; a failure is re-thrown rendered like the reference's Diagnostic::render (pharmsol-dsl/src/diagnostic.rs:220-266):
+// `error[DSL1000|DSL2000]: message`, `  --> line L, column C`, then `  = note / help / suggestion` lines
+CompiledModel compile_source(const std::string& src);
 
 int analytical_kernel_index(const std::string& name);                        // -1 if unknown
 const std::vector<std::string>& analytical_kernel_params(int kernel);

@@ -1095,5 +1095,34 @@ std::string CompiledModel::model_info_json() const {
     return o.str();
 }
 
+static DslError render_diagnostic(const DslError& e, const char* code, const std::string& src) {
+    const std::string what = e.what();
+    const size_t nl = what.find('\n');
+    std::string out = std::string("error[") + code + "]: " + what.substr(0, nl);
+    if (e.pos >= 0) {       // line_info, diagnostic.rs:679-698 (columns count characters, not bytes)
+        const size_t off = std::min((size_t)e.pos, src.size());
+        size_t line = 1, line_start = 0;
+        for (size_t i = 0; i < off; ++i) if (src[i] == '\n') { ++line; line_start = i + 1; }
+        size_t column = 1;
+        for (size_t i = line_start; i < off; ++i) if (((unsigned char)src[i] & 0xC0) != 0x80) ++column;
+        out += "\n  --> line " + std::to_string(line) + ", column " + std::to_string(column);
+    }
+    if (nl != std::string::npos) {      // "  note: ..." / "  help: ..." / "  suggestion: ..." -> "  = note: ..."
+        std::istringstream rest(what.substr(nl + 1));
+        std::string l;
+        while (std::getline(rest, l)) {
+            const size_t a = l.find_first_not_of(' ');
+            out += "\n  = " + (a == std::string::npos ? std::string() : l.substr(a));
+        }
+    }
+    return DslError(out, e.pos);
+}
+
+CompiledModel compile_source(const std::string& src) {
+    ModelAst ast;
+    try { ast = parse_model(src); } catch (const DslError& e) { throw render_diagnostic(e, "DSL1000", src); }
+    try { return compile_model(ast); } catch (const DslError& e) { throw render_diagnostic(e, "DSL2000", src); }
+}
+
 }  // namespace dsl
 }  // namespace pharmsol
