@@ -122,6 +122,7 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
         for (auto& e : c->c.chunk_ev) cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
         cuda_check(cudaEventCreate(&c->c.ev0), "cudaEventCreate");
         cuda_check(cudaEventCreate(&c->c.ev1), "cudaEventCreate");
+        cuda_check(cudaEventCreateWithFlags(&c->c.reset_ev, cudaEventDisableTiming), "cudaEventCreate");
         c->c.err_ctr.reserve(5 * sizeof(unsigned long long));
         cuda_check(cudaMallocHost((void**)&c->c.err_host, 16 * sizeof(unsigned long long)), "cudaMallocHost");
         std::memset(c->c.err_host, 0, 16 * sizeof(unsigned long long));
@@ -504,6 +505,7 @@ int32_t pharmsol_cuda_status_batch_begin(pcu_ctx* ctx, void* stream) {
         cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
         cudaStream_t s = pick_stream(c, stream);
         c.err_ctr.reserve(5 * sizeof(unsigned long long));
+        if (c.status_clean_on && c.status_clean_on != s) cuda_check(cudaStreamWaitEvent(s, c.reset_ev, 0), "wait for queued status reset");
         cuda_check(cudaMemcpyAsync(c.err_ctr.p, c.err_host + 8, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s), "reset status");
         cuda_check(cudaEventRecord(c.ev0, s), "event record");
         c.status_clean_on = nullptr;
@@ -564,6 +566,7 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
             std::memcpy(out, res, (size_t)nsub * nspp * 8);
             const int32_t rc = collect(c, code, pair, true);
             cuda_check(cudaMemcpyAsync(c.err_ctr.p, c.err_host + 8, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream), "reset status");
+            cuda_check(cudaEventRecord(c.reset_ev, c.stream), "event record");
             c.status_clean_on = c.stream;
             return rc;
         }

@@ -44,6 +44,7 @@ struct Ctx {
     static constexpr int kMaxChunks = 16;
     cudaEvent_t chunk_ev[kMaxChunks] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t reset_ev = nullptr;           // recorded behind the status reset that the latency path queues for the next call
     std::mutex mu;
     DevBuf err_ctr;          // [0] first_error (u64)  [1..4] counters
     unsigned long long* err_host = nullptr;   // pinned: [0..4] mirror of err_ctr filled by an async copy queued behind the kernels, [8..12] reset template
