@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PHARMSOL_CUDA_ABI_VERSION 1
+#define PHARMSOL_CUDA_ABI_VERSION 2
 
 /* ---- status codes (== PharmsolError variants, src/error/mod.rs:14-49) ------------------------ */
 enum {
@@ -60,7 +60,9 @@ enum { PCU_ERRMODEL_NONE = 0, PCU_ERRMODEL_ADDITIVE = 1, PCU_ERRMODEL_PROPORTION
 /* OdeSolver (ode/mod.rs:59-84).  The reference offers Bdf | Sdirk(TrBdf2|Esdirk34) | ExplicitRk(Tsit45)
  * through diffsol; this backend offers two explicit pairs, two SDIRK methods and a Rosenbrock method (RODAS4), all
  * register-resident per thread. */
-enum { PCU_SOLVER_DOPRI5 = 0, PCU_SOLVER_TSIT45 = 1, PCU_SOLVER_SDIRK4 = 2, PCU_SOLVER_TRBDF2 = 3, PCU_SOLVER_RODAS4 = 4 };
+enum { PCU_SOLVER_DOPRI5 = 0, PCU_SOLVER_TSIT45 = 1, PCU_SOLVER_SDIRK4 = 2, PCU_SOLVER_TRBDF2 = 3, PCU_SOLVER_RODAS4 = 4,
+       PCU_SOLVER_BDF = 5,        /* OdeSolver::Bdf (the reference default): variable-order NDF/BDF 1-5, the algorithm diffsol's `bdf` documents */
+       PCU_SOLVER_ESDIRK34 = 6 }; /* OdeSolver::Sdirk(SdirkTableau::Esdirk34) */
 /* Analytical `derive` time semantics: sub-interval END (DSL runtime,
  * dsl/native.rs:1903-1916) or sub-interval LENGTH (analytical! macro, analytical/mod.rs:362-364). */
 enum { PCU_COVTIME_INTERVAL_END = 0, PCU_COVTIME_INTERVAL_LENGTH = 1 };
@@ -100,6 +102,20 @@ typedef struct pcu_residual_error_model {
 int32_t pharmsol_cuda_abi_version(void);
 int32_t pharmsol_cuda_device_count(int32_t* n);
 int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out);
+/* SURVEY §8b / north_star "support-point columns shard across the 8 GPUs of one box": ONE host process drives every
+ * listed device.  With such a context
+ *   - pharmsol_cuda_population_create replicates the flattened population on every device;
+ *   - the host-buffer entry points (log_likelihood_matrix, psi, predictions) split the support-point columns into
+ *     n_dev contiguous blocks — psi is F-order (matrix.rs:60), so each block is one contiguous slab of the caller's
+ *     matrix — and every device copies its slab straight to its offset in `out` (no gather needed for a host result);
+ *   - pharmsol_cuda_log_likelihood_matrix_replicated leaves the full psi resident on EVERY device, gathered over NVLink;
+ *   - the *_device / *_peers / *_push entry points and the latency path keep running on device_ids[0].
+ * The first failing pair over all devices is reported (matrix.rs:96-104); SDE random streams are keyed by the global
+ * pair, so results do not depend on the device count.  A device may be listed more than once (several column shards on
+ * one GPU).  rayon callers (`Equation: Sync`) share one context: calls are serialised by its lock. */
+int32_t pharmsol_cuda_ctx_create_multi(const int32_t* device_ids, int32_t n_dev, pcu_ctx** out);
+int32_t pharmsol_cuda_ctx_num_devices(pcu_ctx* ctx);
+int32_t pharmsol_cuda_ctx_device_id(pcu_ctx* ctx, int32_t k);             /* -1 if k is out of range */
 void    pharmsol_cuda_ctx_destroy(pcu_ctx* ctx);
 /* message of the last failure on this thread (valid until the next failing call on the thread) */
 const char* pharmsol_cuda_last_error_message(void);
@@ -239,6 +255,24 @@ int32_t pharmsol_cuda_log_likelihood_matrix_peers(pcu_ctx* ctx, pcu_model* m, pc
                                                   const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                                                   double* const* out_full_peers, int32_t npeers, int64_t ld_out,
                                                   int64_t first_col, void* stream);
+/* Same sharding, gather by the COPY ENGINES instead of by stores from the SMs: the shard is evaluated chunk by chunk
+ * into out_full_peers[self] (this rank's full matrix) and every finished chunk is pushed to the other ranks' matrices
+ * with device-to-device copies over NVLink while the next chunk is computed; `stream` ends up ordered after the last
+ * push.  Closed-form models produce psi at GB/s rates, where 8-byte peer stores (one NVLink packet each) or an NCCL
+ * kernel queued behind the psi CTAs cost 14-40 % of the step; bulk copies on the copy engines overlap with the compute. */
+int32_t pharmsol_cuda_log_likelihood_matrix_push(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                                 const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                                                 double* const* out_full_peers, int32_t npeers, int32_t self, int64_t ld_out,
+                                                 int64_t first_col, void* stream);
+/* Multi-device context: host support points in, the whole psi resident on every device out.
+ *   gather    PCU_GATHER_COPY_ENGINE (chunked pushes, see *_push) or PCU_GATHER_PEER_STORES (see *_peers)
+ *   dev_out   host array of pharmsol_cuda_ctx_num_devices(ctx) pointers; dev_out[k] receives the library-owned
+ *             column-major (nsub x nspp) matrix on device k, valid until the next replicated call on the context
+ * Returns after every device's matrix is complete. */
+enum { PCU_GATHER_COPY_ENGINE = 0, PCU_GATHER_PEER_STORES = 1 };
+int32_t pharmsol_cuda_log_likelihood_matrix_replicated(pcu_ctx* ctx, pcu_model* m, pcu_population* pop,
+                                                       const double* support_points, int64_t nspp, int32_t nparams, int32_t gather,
+                                                       double** dev_out, int32_t* first_error_code, int64_t* first_error_pair);
 int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* first_error_code, int64_t* first_error_pair);
 /* Several asynchronous *_device / *_peers launches, one collect: after this call (which resets the status on
  * `stream`) the launches of the context share one error word and counter set until the next

@@ -70,6 +70,9 @@ def lib():
         "pharmsol_cuda_abi_version": (i32, []),
         "pharmsol_cuda_device_count": (i32, [P(i32)]),
         "pharmsol_cuda_ctx_create": (i32, [i32, P(vp)]),
+        "pharmsol_cuda_ctx_create_multi": (i32, [P(i32), i32, P(vp)]),
+        "pharmsol_cuda_ctx_num_devices": (i32, [vp]),
+        "pharmsol_cuda_ctx_device_id": (i32, [vp, i32]),
         "pharmsol_cuda_ctx_destroy": (None, [vp]),
         "pharmsol_cuda_last_error_message": (cs, []),
         "pharmsol_cuda_launch_count": (i64, [vp]),
@@ -124,6 +127,8 @@ def lib():
         "pharmsol_cuda_log_likelihood_matrix": (i32, [vp, vp, vp, dp, i64, i32, dp, P(i32), P(i64)]),
         "pharmsol_cuda_log_likelihood_matrix_device": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, i64, vp]),
         "pharmsol_cuda_log_likelihood_matrix_peers": (i32, [vp, vp, vp, vp, i64, i64, P(vp), i32, i64, i64, vp]),
+        "pharmsol_cuda_log_likelihood_matrix_push": (i32, [vp, vp, vp, vp, i64, i64, P(vp), i32, i32, i64, i64, vp]),
+        "pharmsol_cuda_log_likelihood_matrix_replicated": (i32, [vp, vp, vp, dp, i64, i32, i32, P(vp), P(i32), P(i64)]),
         "pharmsol_cuda_collect_errors": (i32, [vp, P(i32), P(i64)]),
         "pharmsol_cuda_status_batch_begin": (i32, [vp, vp]),
         "pharmsol_cuda_upload_support_points": (i32, [vp, dp, i64, i32, vp, i64, vp]),
@@ -180,10 +185,25 @@ def device_count():
 
 
 class Context:
-    def __init__(self, device=0):
+    """One device, or — `devices=[...]` — one context driving several devices from this process
+    (pharmsol_cuda_ctx_create_multi: column shards, per-device copies into the caller's matrix)."""
+
+    def __init__(self, device=0, devices=None):
         self.ptr = C.c_void_p()
-        check(lib().pharmsol_cuda_ctx_create(int(device), C.byref(self.ptr)))
-        self.device = int(device)
+        if devices is not None:
+            ids = [int(x) for x in devices]
+            arr = (C.c_int32 * len(ids))(*ids)
+            check(lib().pharmsol_cuda_ctx_create_multi(arr, len(ids), C.byref(self.ptr)))
+            self.devices = ids
+            self.device = ids[0]
+        else:
+            check(lib().pharmsol_cuda_ctx_create(int(device), C.byref(self.ptr)))
+            self.device = int(device)
+            self.devices = [self.device]
+
+    @property
+    def num_devices(self):
+        return lib().pharmsol_cuda_ctx_num_devices(self.ptr)
 
     def close(self):
         if self.ptr:
@@ -220,6 +240,12 @@ _contexts = {}
 
 
 def context(device=0):
+    """One shared Context per device — or per device LIST (a multi-device context, e.g. ``context([0, 1, 2, 3])``)."""
+    if isinstance(device, (list, tuple)):
+        key = tuple(int(x) for x in device)
+        if key not in _contexts:
+            _contexts[key] = Context(devices=list(key))
+        return _contexts[key]
     device = int(device)
     if device not in _contexts:
         _contexts[device] = Context(device)
@@ -518,3 +544,29 @@ def log_likelihood_matrix_peers(ctx, model, pop, spp_soa_ptr, ncols, ld_spp, pee
     arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(q)) for q in peer_ptrs])
     check(lib().pharmsol_cuda_log_likelihood_matrix_peers(ctx.ptr, model.ptr, pop.ptr, C.c_void_p(int(spp_soa_ptr)), int(ncols), int(ld_spp),
                                                           arr, len(peer_ptrs), int(ld_out), int(first_col), C.c_void_p(int(stream) or None)))
+
+
+def log_likelihood_matrix_push(ctx, model, pop, spp_soa_ptr, ncols, ld_spp, peer_ptrs, self_index, ld_out, first_col, stream=0):
+    """Asynchronous chunked launch into peer_ptrs[self_index] (a full matrix) + copy-engine pushes of every finished
+    chunk to the other ranks' matrices (pharmsol_cuda_log_likelihood_matrix_push)."""
+    arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(q)) for q in peer_ptrs])
+    check(lib().pharmsol_cuda_log_likelihood_matrix_push(ctx.ptr, model.ptr, pop.ptr, C.c_void_p(int(spp_soa_ptr)), int(ncols), int(ld_spp),
+                                                         arr, len(peer_ptrs), int(self_index), int(ld_out), int(first_col),
+                                                         C.c_void_p(int(stream) or None)))
+
+
+GATHER_COPY_ENGINE, GATHER_PEER_STORES = 0, 1
+
+
+def log_likelihood_matrix_replicated(ctx, model, pop, support_points, gather=GATHER_COPY_ENGINE):
+    """Multi-device context: host support points in, the whole psi resident on every device out.
+    Returns the list of device pointers (one column-major (nsub, nspp) matrix per device, library-owned)."""
+    spp = np.ascontiguousarray(support_points, dtype=np.float64)
+    nspp, npar = spp.shape
+    n = ctx.num_devices
+    ptrs = (C.c_void_p * n)()
+    code, pair = C.c_int32(0), C.c_int64(-1)
+    rc = lib().pharmsol_cuda_log_likelihood_matrix_replicated(ctx.ptr, model.ptr, pop.ptr, _dp(spp), nspp, npar, int(gather), ptrs, C.byref(code), C.byref(pair))
+    if rc != 0:
+        raise PharmsolError(rc, _msg(), pair.value if pair.value >= 0 else None)
+    return [int(q or 0) for q in ptrs]

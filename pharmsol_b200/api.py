@@ -235,16 +235,16 @@ class AssayErrorModels:
 # equations
 # ---------------------------------------------------------------------------------------------
 class OdeSolver:
-    """ode/mod.rs:59-84.  The reference's solvers come from diffsol; this backend provides two
-    explicit pairs and two implicit (stiff) methods.  `Bdf` (the reference default for stiff
-    problems) selects the Rosenbrock method RODAS4, `Esdirk34` the order-4 SDIRK."""
+    """ode/mod.rs:59-84.  The reference's solvers come from diffsol: Bdf (default), Sdirk(TrBdf2 | Esdirk34),
+    ExplicitRk(Tsit45) — each has a device counterpart of the same published method (psi_bdf.cuh, psi_stiff.cuh,
+    psi_ode.cuh); Dopri5, Sdirk4 and the Rosenbrock method Rodas4 are this backend's own additions."""
     Dopri5 = 0
     Tsit45 = 1
     Sdirk4 = 2
     TrBdf2 = 3
     Rodas4 = 4      # Rosenbrock (linearly implicit, no Newton iteration): the stiff workhorse on the GPU
-    Bdf = 4
-    Esdirk34 = 2
+    Bdf = 5         # variable-order NDF/BDF 1-5 (the algorithm diffsol's `bdf` documents)
+    Esdirk34 = 6    # ESDIRK3(4) of Jorgensen, Kristensen & Thomsen (diffsol `esdirk34`)
 
 
 class CovTime:
@@ -393,7 +393,8 @@ class Equation:
 
     def population(self, data: Data, error_models: AssayErrorModels | None):
         dense = error_models.bound(self.output_names()) if error_models is not None else None
-        key = (id(data), repr(dense))
+        dev = self.device
+        key = (id(data), repr(dense), tuple(dev) if isinstance(dev, (list, tuple)) else dev)
         pop = self._pops.get(key)
         if pop is None:
             if len(self._pops) > 8:
@@ -750,7 +751,7 @@ class ResidentPsi:
     """
 
     def __init__(self, equation: Equation, data: Data, support_points, error_models: AssayErrorModels, device=None, shard=True,
-                 peer_stores="auto", gather_overlap="auto"):
+                 peer_stores="auto", gather_overlap="auto", gather="auto"):
         import torch
         import torch.distributed as dist
         from .sharding import ShardedPsi
@@ -765,11 +766,18 @@ class ResidentPsi:
         spp = np.ascontiguousarray(support_points, dtype=np.float64)
         self.nspp, self.nparams = spp.shape
         self.nsub = self.pop.nsubjects
-        if peer_stores == "auto":
-            # 8-byte peer stores are one NVLink packet each: they win when a pair costs microseconds (ODE / SDE: C2 on
-            # 8 GPUs 42.8 ms fused vs 44.3 ms with NCCL) and lose when psi is produced at GB/s rates (closed forms: C3 on
-            # 8 GPUs 63.5 ms fused vs 57.0 ms with the bulk NCCL all-gather)
-            peer_stores = equation.kind() != EqnKind.Analytical
+        # How the column slabs reach every rank (N > 1):
+        #   "peer"  the psi kernel stores every result into all ranks' matrices (8-byte stores, one NVLink packet each):
+        #           wins when a pair costs microseconds (ODE / SDE: C2 on 8 GPUs 42.8 ms fused vs 44.3 ms with NCCL);
+        #   "push"  finished column chunks are pushed to the peers by the copy engines while the next chunk computes:
+        #           for closed forms, whose psi is produced at GB/s rates (C3 on 8 GPUs: 63.5 ms with peer stores,
+        #           37.8 ms with a bulk NCCL all-gather whose kernel queues behind the psi CTAs);
+        #   "nccl"  one in-place all_gather_into_tensor after the kernel.
+        if gather == "auto" and peer_stores != "auto":
+            gather = "peer" if peer_stores else "nccl"
+        if gather == "auto":
+            gather = "push" if equation.kind() == EqnKind.Analytical else "peer"
+        peer_stores = gather in ("peer", "push")
         multi = shard and dist.is_available() and dist.is_initialized()
         if gather_overlap == "auto":
             # Phased gather (evaluate 7/8 of this rank's columns, all-gather them while the last 1/8 is evaluated;
@@ -780,6 +788,9 @@ class ResidentPsi:
         gather_overlap = bool(gather_overlap) and (not peer_stores) and multi
         self.sharded = ShardedPsi(self.nsub, self.nspp, self.device, peer_stores=bool(peer_stores), tail_fraction=0.125 if gather_overlap else 0.0) if multi \
             else _SingleRank(self.nsub, self.nspp, self.device)
+        if multi and peer_stores and getattr(self.sharded, "peer_ptrs", None) is None:
+            gather = "nccl"          # no peer mapping available: the NCCL all-gather takes over
+        self.gather_mode = gather if (multi and self.sharded.world > 1) else None
         self.ranges = [r for r in self.sharded.local_ranges]
         self.first_col = self.ranges[0][0]
         self.ncols = sum(hi - lo for lo, hi in self.ranges)
@@ -803,6 +814,9 @@ class ResidentPsi:
             return
         spp_ptr = self.spp_soa.data_ptr() + 8 * offset
         peers = getattr(self.sharded, "peer_ptrs", None)
+        if peers is not None and self.gather_mode == "push":      # copy-engine pushes of finished chunks
+            _lib.log_likelihood_matrix_push(self.ctx, self.eq._model, self.pop, spp_ptr, hi - lo, self.ld_spp, peers, self.sharded.rank, self.nsub, lo, self._stream())
+            return
         if peers is not None:      # fused all-gather: results go straight into every rank's full matrix
             _lib.log_likelihood_matrix_peers(self.ctx, self.eq._model, self.pop, spp_ptr, hi - lo, self.ld_spp, peers, self.nsub, lo, self._stream())
             return

@@ -22,6 +22,7 @@
 #include "psi_analytical.cuh"
 #include "psi_ode.cuh"
 #include "psi_stiff.cuh"
+#include "psi_bdf.cuh"
 #include "psi_sde.cuh"
 
 namespace psi {
@@ -43,9 +44,16 @@ struct OdeRhs {
 
 // The solver is a compile-time parameter of the kernel so the explicit kernels do not pay the
 // register cost of the implicit ones (Jacobian + LU) and vice versa.
+// Memory a solver keeps between two integrate-to-stop calls of one occasion (only the multistep method has any).
+template <int SOLVER, int N> struct SolverMem { using type = NoSolverMem; };
+template <int N> struct SolverMem<SOLVER_BDF, N> { using type = BdfState<N>; };
+
 template <class M, int SOLVER>
-PSI_DEV int ode_advance(OdeState<M::NSTATE>& st, double tstop, OdeRhs<M>& f, const RunOpts& opt, Counters& cnt) {
-    if constexpr (SOLVER == SOLVER_TSIT5) return erk_integrate_to<Tsit5, M::NSTATE>(st, tstop, f, opt, cnt);
+PSI_DEV int ode_advance(OdeState<M::NSTATE>& st, typename SolverMem<SOLVER, M::NSTATE>::type& mem, double tstop, OdeRhs<M>& f, const RunOpts& opt,
+                        Counters& cnt) {
+    if constexpr (SOLVER == SOLVER_BDF) return bdf_integrate_to<M::NSTATE>(st, mem, tstop, f, opt, cnt);
+    else if constexpr (SOLVER == SOLVER_ESDIRK34) return esdirk34_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
+    else if constexpr (SOLVER == SOLVER_TSIT5) return erk_integrate_to<Tsit5, M::NSTATE>(st, tstop, f, opt, cnt);
     else if constexpr (SOLVER == SOLVER_SDIRK4) return sdirk4_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
     else if constexpr (SOLVER == SOLVER_TRBDF2) return trbdf2_integrate_to<M::NSTATE>(st, tstop, f, opt, cnt);
     else if constexpr (SOLVER == SOLVER_RODAS4) return rodas4_integrate_to<M::NSTATE, M::RHS_TIME_DEP>(st, tstop, f, opt, cnt);
@@ -117,6 +125,7 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
         // ---- ODE solver state -------------------------------------------------------------------
         [[maybe_unused]] OdeState<AtLeast1<NS>::v> st;
         [[maybe_unused]] OdeRhs<M> rhs{c};
+        [[maybe_unused]] typename SolverMem<(M::KIND == 0 ? SOLVER : 0), AtLeast1<NS>::v>::type solver_mem;
         [[maybe_unused]] int bnd = 0, bnd_end = 0, abc = 0;
         if constexpr (M::KIND == 1) {
             abc = __ldg(pop.bnd_offsets + occ);
@@ -223,7 +232,7 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                         }
                         segment_rates<NR>(inf, st.t, c.rate);    // constant on [st.t, stop): right-continuous at
                                                                  // st.t, left-continuous at stop (closure.rs:43-51)
-                        const int rc = ode_advance<M, SOLVER>(st, stop, rhs, opt, cnt);
+                        const int rc = ode_advance<M, SOLVER>(st, solver_mem, stop, rhs, opt, cnt);
                         if (rc != ST_OK) { if (status == ST_OK) status = rc; st.t = tn; break; }
                         if (is_bnd) st.have_k1 = false;          // RHS discontinuity: refresh dy (ode/mod.rs:568-586)
                     }

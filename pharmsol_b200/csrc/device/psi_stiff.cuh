@@ -18,15 +18,18 @@
 
 namespace psi {
 
-// LU of an N x N matrix held in registers.  swaps bit (k*N + i): rows k and i swapped at column k.
+// LU of an N x N matrix held in registers.  swaps[k] bit i: rows k and i swapped at column k (one mask per
+// column, statically indexed under full unrolling, so any N <= 32 is correct).
 template <int N>
 struct SmallLU {
+    static_assert(N >= 1 && N <= 32, "SmallLU keeps one 32-bit swap mask per column");
     double a[N * N];
-    unsigned long long swaps;
+    unsigned int swaps[N];
     bool singular;
 
     PSI_DEV void factor() {
-        swaps = 0ull;
+#pragma unroll
+        for (int k = 0; k < N; ++k) swaps[k] = 0u;
         singular = false;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
@@ -34,7 +37,7 @@ struct SmallLU {
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = fabs(a[i * N + k]) > fabs(a[k * N + k]);
-                swaps |= sw ? (1ull << (k * N + i)) : 0ull;
+                swaps[k] |= sw ? (1u << i) : 0u;
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const double u = a[k * N + j], v = a[i * N + j];
@@ -60,7 +63,7 @@ struct SmallLU {
         for (int k = 0; k < N; ++k) {
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
-                const bool sw = (swaps >> (k * N + i)) & 1ull;
+                const bool sw = (swaps[k] >> i) & 1u;
                 const double u = b[k], v = b[i];
                 b[k] = sw ? v : u;
                 b[i] = sw ? u : v;

@@ -105,7 +105,10 @@ struct PopView {
     int32_t pad;
 };
 
-enum : int { SOLVER_DOPRI5 = 0, SOLVER_TSIT5 = 1, SOLVER_SDIRK4 = 2, SOLVER_TRBDF2 = 3, SOLVER_RODAS4 = 4 };
+// 0-4 are this backend's own integrators; 5-6 carry the reference's remaining solver names (ode/mod.rs:59-84):
+// Bdf = variable-order NDF/BDF 1-5 (diffsol `bdf`, the default of every reference ODE), Esdirk34 = diffsol `esdirk34`.
+enum : int { SOLVER_DOPRI5 = 0, SOLVER_TSIT5 = 1, SOLVER_SDIRK4 = 2, SOLVER_TRBDF2 = 3, SOLVER_RODAS4 = 4, SOLVER_BDF = 5, SOLVER_ESDIRK34 = 6,
+             SOLVER_COUNT = 7 };
 enum : int { COVTIME_INTERVAL_END = 0, COVTIME_INTERVAL_LENGTH = 1 };
 enum : int { SDE_MEAN_PREDICTION = 0, SDE_PARTICLE_FILTER = 1 };
 enum : int { EM_REFERENCE_ADAPTIVE = 0, EM_FIXED_STEP = 1 };

@@ -4,13 +4,25 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <thread>
+#include <vector>
+
+#include <unistd.h>
 
 #include "../../../include/pharmsol_cuda.h"
 #include "runtime.hpp"
 
 using namespace pharmsol;
 
-struct pcu_ctx { Ctx c; };
+// A context is one device (`c`) or, from pharmsol_cuda_ctx_create_multi, `c` (= device_ids[0]) plus one Ctx per further
+// device: streams, events, staging buffers and the status word are per device; the caller-facing lock is c.mu.
+struct pcu_ctx {
+    Ctx c;
+    std::vector<std::unique_ptr<Ctx>> more;
+    int ndev() const { return 1 + (int)more.size(); }
+    Ctx& dev(int k) { return k == 0 ? c : *more[(size_t)k - 1]; }
+    bool peer_enabled = false;
+};
 struct pcu_model { Model m; };
 struct pcu_subject_builder { SubjectBuilder b; std::string error; explicit pcu_subject_builder(const char* id) : b(id) {} };
 struct pcu_subject { Subject s; };
@@ -107,34 +119,81 @@ int32_t pharmsol_cuda_device_count(int32_t* n) {
     });
 }
 
+static void init_ctx(Ctx& c, int32_t device) {
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10) throw CudaError(std::string("device `") + prop.name + "` is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this backend is built for sm_100a only");
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    cuda_check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_check(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : c.chunk_ev) cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventCreate(&c.ev0), "cudaEventCreate");
+    cuda_check(cudaEventCreate(&c.ev1), "cudaEventCreate");
+    cuda_check(cudaEventCreateWithFlags(&c.reset_ev, cudaEventDisableTiming), "cudaEventCreate");
+    c.err_ctr.reserve(5 * sizeof(unsigned long long));
+    cuda_check(cudaMallocHost((void**)&c.err_host, 16 * sizeof(unsigned long long)), "cudaMallocHost");
+    std::memset(c.err_host, 0, 16 * sizeof(unsigned long long));
+    c.err_host[8] = ~0ull;
+    cuda_check(cudaMallocHost((void**)&c.small_host, Ctx::kSmallIn + Ctx::kSmallOut), "cudaMallocHost");
+}
+
 int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
     return guarded([&] {
         if (!out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
-        cuda_check(cudaSetDevice(device), "cudaSetDevice");
-        cudaDeviceProp prop;
-        cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
-        if (prop.major < 10) throw CudaError(std::string("device `") + prop.name + "` is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this backend is built for sm_100a only");
         std::unique_ptr<pcu_ctx> c(new pcu_ctx());      // ~Ctx releases whatever was created if a later step throws
-        c->c.device = device;
-        c->c.sm_count = prop.multiProcessorCount;
-        cuda_check(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        cuda_check(cudaStreamCreateWithFlags(&c->c.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        for (auto& e : c->c.chunk_ev) cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-        cuda_check(cudaEventCreate(&c->c.ev0), "cudaEventCreate");
-        cuda_check(cudaEventCreate(&c->c.ev1), "cudaEventCreate");
-        cuda_check(cudaEventCreateWithFlags(&c->c.reset_ev, cudaEventDisableTiming), "cudaEventCreate");
-        c->c.err_ctr.reserve(5 * sizeof(unsigned long long));
-        cuda_check(cudaMallocHost((void**)&c->c.err_host, 16 * sizeof(unsigned long long)), "cudaMallocHost");
-        std::memset(c->c.err_host, 0, 16 * sizeof(unsigned long long));
-        c->c.err_host[8] = ~0ull;
-        cuda_check(cudaMallocHost((void**)&c->c.small_host, Ctx::kSmallIn + Ctx::kSmallOut), "cudaMallocHost");
+        init_ctx(c->c, device);
         *out = c.release();
         return (int32_t)PCU_OK;
     });
 }
+
+// ctx_create(const int* device_ids, int n_dev, ...).  One host process drives every listed device: the
+// host-buffer entry points split the support-point columns into n_dev contiguous blocks (matrix.rs:60 F-order => one
+// contiguous slab of `out` per device), each device copies its slab straight into the caller's matrix, and
+// pharmsol_cuda_log_likelihood_matrix_replicated leaves the whole psi resident on every device (gathered over
+// NVLink).  A device may be listed more than once (two shards on one GPU: the single-GPU test of this path).
+int32_t pharmsol_cuda_ctx_create_multi(const int32_t* device_ids, int32_t n_dev, pcu_ctx** out) {
+    return guarded([&] {
+        if (!out || !device_ids || n_dev < 1 || n_dev > 64) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::unique_ptr<pcu_ctx> c(new pcu_ctx());
+        init_ctx(c->c, device_ids[0]);
+        for (int32_t k = 1; k < n_dev; ++k) {
+            c->more.emplace_back(new Ctx());
+            init_ctx(*c->more.back(), device_ids[k]);
+        }
+        // peer access between every pair of distinct devices (NVLink / NVSwitch): peer stores from the psi kernel and
+        // device-to-device pushes by the copy engines both need it
+        bool all = true;
+        for (int a = 0; a < n_dev; ++a) {
+            for (int b = 0; b < n_dev; ++b) {
+                if (device_ids[a] == device_ids[b]) continue;
+                int can = 0;
+                cuda_check(cudaDeviceCanAccessPeer(&can, device_ids[a], device_ids[b]), "cudaDeviceCanAccessPeer");
+                if (!can) { all = false; continue; }
+                cuda_check(cudaSetDevice(device_ids[a]), "cudaSetDevice");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[b], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+                else cuda_check(e, "cudaDeviceEnablePeerAccess");
+            }
+        }
+        c->peer_enabled = all;
+        cuda_check(cudaSetDevice(device_ids[0]), "cudaSetDevice");
+        *out = c.release();
+        return (int32_t)PCU_OK;
+    });
+}
+int32_t pharmsol_cuda_ctx_num_devices(pcu_ctx* ctx) { return ctx ? ctx->ndev() : 0; }
+int32_t pharmsol_cuda_ctx_device_id(pcu_ctx* ctx, int32_t k) { return (ctx && k >= 0 && k < ctx->ndev()) ? ctx->dev(k).device : -1; }
 void pharmsol_cuda_ctx_destroy(pcu_ctx* ctx) { delete ctx; }
 const char* pharmsol_cuda_last_error_message(void) { return last_error().c_str(); }
-int64_t pharmsol_cuda_launch_count(pcu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+int64_t pharmsol_cuda_launch_count(pcu_ctx* ctx) {
+    if (!ctx) return 0;
+    int64_t n = 0;
+    for (int k = 0; k < ctx->ndev(); ++k) n += ctx->dev(k).launches;
+    return n;
+}
 double pharmsol_cuda_last_kernel_ms(pcu_ctx* ctx) { return ctx ? ctx->c.last_kernel_ms : 0.0; }
 int32_t pharmsol_cuda_last_counters(pcu_ctx* ctx, uint64_t out[4]) {
     if (!ctx || !out) return PCU_ERR_INVALID_ARGUMENT;
@@ -273,7 +332,7 @@ static pcu_model* make_model(const std::string& source) {
     m->m.opts.em_mode = psi::EM_REFERENCE_ADAPTIVE;
     m->m.info_json = m->m.cm.model_info_json();
     std::vector<std::pair<int, std::string>> entries;
-    if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < 5; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
+    if (m->m.cm.kind == dsl::ModelKind::Ode) for (int s = 0; s < psi::SOLVER_COUNT; ++s) entries.emplace_back(s, entry_name(m->m.cm.id, s));
     else entries.emplace_back(0, entry_name(m->m.cm.id, 0));
     m->m.source_cache = m->m.cm.cuda_source(entries, false);
     return m.release();
@@ -292,7 +351,7 @@ int32_t pharmsol_cuda_model_export_artifact(pcu_model* m, const char* path, cons
         std::vector<int> list;
         if (nsolvers == 0) list.push_back(effective_solver(m->m));
         for (int i = 0; i < nsolvers; ++i) {
-            if (solvers[i] < 0 || solvers[i] > 4) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+            if (solvers[i] < 0 || solvers[i] >= psi::SOLVER_COUNT) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
             const int sv = m->m.cm.kind == dsl::ModelKind::Ode ? solvers[i] : 0;
             if (std::find(list.begin(), list.end(), sv) == list.end()) list.push_back(sv);
         }
@@ -307,6 +366,7 @@ int32_t pharmsol_cuda_model_load_artifact(pcu_ctx*, const char* path, pcu_model*
         std::unique_ptr<pcu_model> m(make_model(a.dsl_source));
         try {
             apply_artifact_settings(a.settings, m->m.opts);
+        } catch (const PharmsolError& e) { throw PharmsolError(PCU_ERR_OTHER, std::string("artifact ") + path + ": " + e.what());
         } catch (const std::exception&) { throw PharmsolError(PCU_ERR_OTHER, std::string("artifact ") + path + " has malformed settings"); }
         // Device code compiled against another engine build (other kernel-parameter layout) is not trusted: the
         // model then takes the usual registry / cache / NVRTC route from the DSL source it carries.
@@ -342,7 +402,7 @@ const char* pharmsol_cuda_model_info_json(const pcu_model* m) { return m ? m->m.
 const char* pharmsol_cuda_model_cuda_source(const pcu_model* m) { return m ? m->m.source_cache.c_str() : ""; }
 const char* pharmsol_cuda_model_id(const pcu_model* m) { return m ? m->m.cm.id.c_str() : ""; }
 int32_t pharmsol_cuda_model_set_solver(pcu_model* m, int32_t solver, double rtol, double atol) {
-    if (!m || solver < 0 || solver > 4 || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
+    if (!m || solver < 0 || solver >= psi::SOLVER_COUNT || !(rtol > 0) || !(atol > 0)) return PCU_ERR_INVALID_ARGUMENT;
     m->m.opts.solver = solver; m->m.opts.rtol = rtol; m->m.opts.atol = atol;
     return PCU_OK;
 }
@@ -377,10 +437,15 @@ int32_t pharmsol_cuda_model_precompile_to_cache(pcu_model* m, int32_t solver) {
         const std::string name = entry_name(m->m.cm.id, solver);
         auto cubin = nvrtc_compile_cubin(m->m.cm.cuda_source({{solver, name}}, false), name);
         const std::string path = cubin_cache_path(m->m.cm.id, solver);
-        FILE* f = std::fopen(path.c_str(), "wb");
-        if (!f) throw PharmsolError(PCU_ERR_OTHER, "cannot write " + path);
-        std::fwrite(cubin.data(), 1, cubin.size(), f);
-        std::fclose(f);
+        // write-then-rename, like get_kernel: a concurrent reader never sees a half-written cubin
+        const std::string tmp = path + ".tmp." + std::to_string((long long)::getpid());
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f) throw PharmsolError(PCU_ERR_OTHER, "cannot write " + tmp);
+        const size_t nw = std::fwrite(cubin.data(), 1, cubin.size(), f);
+        if (std::fclose(f) != 0 || nw != cubin.size() || std::rename(tmp.c_str(), path.c_str()) != 0) {
+            std::remove(tmp.c_str());
+            throw PharmsolError(PCU_ERR_OTHER, "cannot write " + path);
+        }
         return (int32_t)PCU_OK;
     });
 }
@@ -398,6 +463,10 @@ int32_t pharmsol_cuda_population_create(pcu_ctx* ctx, const pcu_model* m, const 
             p->p.device = ctx->c.device;
             if (ems && n_ems > 0) { p->em = to_models(ems, n_ems); p->has_em = true; }
             p->p.flat = flatten_population(p->p.data, p->p.labels, p->has_em ? &p->em : nullptr);
+            for (int k = 1; k < ctx->ndev(); ++k) {       // one replica per further device of a multi-device context
+                p->p.replicas.emplace_back(new PopReplica());
+                p->p.replicas.back()->device = ctx->dev(k).device;
+            }
             p->p.upload();
         } catch (...) { delete p; throw; }
         *out = p;
@@ -411,12 +480,17 @@ int32_t pharmsol_cuda_population_set_error_models(pcu_population* pop, const pcu
         pop->has_em = ems && n > 0;
         if (pop->has_em) pop->em = to_models(ems, n);
         pop->p.flat = flatten_population(pop->p.data, pop->p.labels, pop->has_em ? &pop->em : nullptr);
+        // The upload overwrites the events in place with a blocking copy on the legacy stream, which does not order
+        // against the contexts' non-blocking streams or a caller's stream: drain the device first so a psi kernel still
+        // in flight from the asynchronous *_device / *_peers entry points never reads a half-updated timeline.
+        cuda_check(cudaDeviceSynchronize(), "synchronize before re-flattening the population");
         pop->p.upload();
         return (int32_t)PCU_OK;
     });
 }
 void pharmsol_cuda_population_destroy(pcu_population* pop) {
     if (!pop) return;
+    cudaSetDevice(pop->p.device);
     pop->p.dev.release();
     delete pop;
 }
@@ -487,6 +561,21 @@ int32_t pharmsol_cuda_log_likelihood_matrix_peers(pcu_ctx* ctx, pcu_model* m, pc
         return (int32_t)PCU_OK;
     });
 }
+// Column-sharded psi with a copy-engine push gather (one process per GPU: the peers' matrices are mapped into this
+// process by CUDA IPC / symmetric memory; one process for all GPUs: cudaDeviceEnablePeerAccess).
+int32_t pharmsol_cuda_log_likelihood_matrix_push(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev, int64_t ncols,
+                                                 int64_t ld_spp, double* const* out_full_peers, int32_t npeers, int32_t self, int64_t ld_out,
+                                                 int64_t first_col, void* stream) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp_soa_dev || !out_full_peers || npeers < 1 || npeers > 64 || self < 0 || self >= npeers || ld_out < pop->p.flat.nsub)
+            return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        for (int r = 0; r < npeers; ++r) if (!out_full_peers[r]) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        launch_psi_push(ctx->c, m->m, pop->p, pop->p.view, spp_soa_dev, ncols, ld_spp, out_full_peers, npeers, self, ld_out, first_col, pick_stream(ctx->c, stream));
+        return (int32_t)PCU_OK;
+    });
+}
 int32_t pharmsol_cuda_predictions_device(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp_soa_dev, int64_t ncols,
                                          int64_t ld_spp, double* pred_dev, int64_t ld_pred, double* ll_dev, int64_t ld_out, void* stream) {
     return guarded([&] {
@@ -524,6 +613,86 @@ int32_t pharmsol_cuda_collect_errors(pcu_ctx* ctx, int32_t* code, int64_t* pair)
     });
 }
 
+// ---- host-buffer calls ---------------------------------------------------------------------------------------
+// One device's share of a host-buffer psi call: H2D of its support-point rows, on-device transpose, the column chunks
+// pipelined against their copy-back (psi is column-major, so a block of columns is one contiguous slab of `out`; a
+// chunk is copied device -> host on the copy stream while the next one is computed and only the LAST copy is exposed).
+//  * closed-form models (kernel short next to the copy): up to 16 equal chunks of >= 2 MB and >= 128 columns — for a
+//    1000 x 1000 one-compartment matrix the 8 MB copy-back is otherwise longer than the kernel;
+//  * adaptive ODE / SDE models (kernel long next to the copy): two chunks, 7/8 + 1/8 of the columns
+//    (profiles/r01_tuning.md).
+// `first_col` = global index of the shard's first column (error pairs and SDE random streams are global).
+static int32_t matrix_host_shard(Ctx& c, Model& m, Population& pop, const psi::PopView& view, const double* spp_rows, int64_t ncols, int32_t np,
+                                 double* out, int64_t first_col, bool exponentiate, int32_t* code, int64_t* pair) {
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    c.status_batch = false;      // a host-buffer call resets and reads the status itself
+    const int64_t nsub = pop.flat.nsub;
+    c.spp_soa.reserve((size_t)ncols * np * 8);
+    c.out.reserve((size_t)nsub * ncols * 8);
+    c.spp_rows.reserve((size_t)ncols * np * 8);
+    cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp_rows, (size_t)ncols * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+    launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), ncols, np, ncols, c.stream);
+    c.launches += 1;
+    const std::vector<int64_t> cuts = column_chunks(m, nsub, ncols, Ctx::kMaxChunks);
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int64_t c0 = cuts[k], c1 = cuts[k + 1];
+        double* slab = c.out.as<double>() + c0 * nsub;
+        launch_psi(c, m, pop, c.spp_soa.as<double>() + c0, c1 - c0, ncols, slab, nsub, nullptr, 0, first_col + c0, c.stream, nullptr, k == 0, nullptr, 0, &view);
+        if (exponentiate) { launch_exp_inplace(slab, nsub * (c1 - c0), c.stream); c.launches += 1; }
+        cuda_check(cudaEventRecord(c.chunk_ev[k], c.stream), "chunk event");
+        cuda_check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[k], 0), "chunk wait");
+        cuda_check(cudaMemcpyAsync(out + c0 * nsub, slab, (size_t)(nsub * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "D2H psi");
+    }
+    cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
+    cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+    cuda_check(cudaStreamSynchronize(c.copy_stream), "synchronize");
+    return collect(c, code, pair, true);
+}
+
+// Contiguous column blocks of a multi-device call: block k = [k*per, min((k+1)*per, nspp)).
+static int64_t shard_columns(int64_t nspp, int ndev) { return (nspp + ndev - 1) / ndev; }
+static bool use_all_devices(const pcu_ctx* ctx, int64_t nspp) { return ctx->ndev() > 1 && nspp >= 32ll * ctx->ndev(); }
+
+struct ShardResult {
+    int32_t rc = PCU_OK, code = 0;
+    int64_t pair = -1;
+    std::string msg;
+};
+// Run fn(k) for every device of the context concurrently (device 0 on the calling thread, the others on their own host
+// threads: copies from pageable caller memory block the issuing thread, so one thread per device keeps the devices
+// busy at the same time) and fold the results: the FIRST failing pair over all shards wins (matrix.rs:96-104);
+// library-level failures (CUDA, compile) win over pair errors.
+extern "C++" {
+template <class F>
+static int32_t for_each_device(pcu_ctx* ctx, F&& fn, int32_t* code, int64_t* pair) {
+    const int n = ctx->ndev();
+    std::vector<ShardResult> res((size_t)n);
+    auto run = [&](int k) {
+        ShardResult& r = res[(size_t)k];
+        r.rc = guarded([&] { return fn(k, &r.code, &r.pair); });
+        if (r.rc != PCU_OK) r.msg = last_error();
+    };
+    std::vector<std::thread> workers;
+    for (int k = 1; k < n; ++k) workers.emplace_back(run, k);
+    run(0);
+    for (auto& w : workers) w.join();
+    cudaSetDevice(ctx->c.device);
+    int32_t out_code = 0;
+    int64_t out_pair = -1;
+    const ShardResult* hard = nullptr;
+    const ShardResult* first = nullptr;
+    for (const auto& r : res) {
+        if (r.rc != PCU_OK && r.code == 0 && !hard) hard = &r;          // not a pair error
+        if (r.code != 0 && (!first || r.pair < first->pair)) first = &r;
+    }
+    if (hard) { set_last_error(hard->msg); if (code) *code = 0; if (pair) *pair = -1; return hard->rc; }
+    if (first) { out_code = first->code; out_pair = first->pair; set_last_error(first->msg); }
+    if (code) *code = out_code;
+    if (pair) *pair = out_pair;
+    return first ? first->rc : (int32_t)PCU_OK;
+}
+}  // extern "C++"
+
 static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp, int32_t np,
                            double* out, int32_t* code, int64_t* pair, bool exponentiate) {
     return guarded([&] {
@@ -539,8 +708,15 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
         c.status_batch = false;      // a host-buffer call resets and reads the status itself
         const int64_t nsub = pop->p.flat.nsub;
         if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
-        c.spp_soa.reserve((size_t)nspp * np * 8);
-        c.out.reserve((size_t)nsub * nspp * 8);
+        if (use_all_devices(ctx, nspp)) {
+            if ((int)pop->p.replicas.size() + 1 != ctx->ndev()) throw PharmsolError(PCU_ERR_OTHER, "population was created for another context (device list differs)");
+            const int64_t per = shard_columns(nspp, ctx->ndev());
+            return for_each_device(ctx, [&](int k, int32_t* scode, int64_t* spair) {
+                const int64_t lo = std::min<int64_t>(nspp, k * per), hi = std::min<int64_t>(nspp, lo + per);
+                if (hi <= lo) return (int32_t)PCU_OK;
+                return matrix_host_shard(ctx->dev(k), m->m, pop->p, pop->p.view_on(k), spp + lo * np, hi - lo, np, out + lo * nsub, lo, exponentiate, scode, spair);
+            }, code, pair);
+        }
         if (c.small_host && (size_t)nspp * np * 8 <= Ctx::kSmallIn && (size_t)nsub * nspp * 8 <= Ctx::kSmallOut) {
             // Latency-bound call (an optimiser's cost function: one or a few support points).  Support points are
             // transposed on the host into pinned memory; results and status come back through pinned memory with one
@@ -549,6 +725,8 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
             // stores psi directly in the pinned host buffer (unified addressing), which removes both DMA copies;
             // measured on the 32 x 64 criterion shapes, beyond a few KB the copy engines are faster than PCIe stores
             // from the SMs (profiles/r01_tuning.md).
+            c.spp_soa.reserve((size_t)nspp * np * 8);
+            c.out.reserve((size_t)nsub * nspp * 8);
             double* in = c.small_host;
             double* res = c.small_host + Ctx::kSmallIn / 8;
             for (int64_t j = 0; j < nspp; ++j)
@@ -570,41 +748,7 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
             c.status_clean_on = c.stream;
             return rc;
         }
-        c.spp_rows.reserve((size_t)nspp * np * 8);
-        cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
-        launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
-        c.launches += 1;
-        // Pipeline over column chunks: psi is column-major, so a block of columns is one contiguous slab; a chunk is
-        // copied device -> host on the copy stream while the next one is computed, and only the LAST copy is exposed.
-        //  * closed-form models (kernel short next to the copy): up to 16 equal chunks of >= 2 MB and >= 128 columns —
-        //    for a 1000 x 1000 one-compartment matrix the 8 MB copy-back is otherwise longer than the kernel;
-        //  * adaptive ODE / SDE models (kernel long next to the copy): every extra launch costs a probe + sort of the
-        //    work-balanced column order and a kernel tail, so two chunks, 7/8 + 1/8 of the columns: the big copy hides
-        //    behind the small chunk's compute and the exposed copy is 1/8 of the matrix (profiles/r01_tuning.md).
-        const int64_t bytes = nsub * nspp * 8;
-        std::vector<int64_t> cuts{0};
-        if (m->m.cm.kind == dsl::ModelKind::Analytical) {
-            int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(Ctx::kMaxChunks, bytes / (2ll << 20)));
-            nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, nspp / 128));
-            const int64_t per = ((nspp + nchunk - 1) / nchunk + 127) / 128 * 128;      // chunk starts stay 1 KB aligned in the SoA rows
-            for (int64_t c0 = per; c0 < nspp; c0 += per) cuts.push_back(c0);
-        } else if (bytes >= (16ll << 20) && nspp >= 8192) {
-            cuts.push_back((nspp - nspp / 8) / 128 * 128);
-        }
-        cuts.push_back(nspp);
-        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-            const int64_t c0 = cuts[k], c1 = cuts[k + 1];
-            double* slab = c.out.as<double>() + c0 * nsub;
-            launch_psi(c, m->m, pop->p, c.spp_soa.as<double>() + c0, c1 - c0, nspp, slab, nsub, nullptr, 0, c0, c.stream, nullptr, k == 0);
-            if (exponentiate) { launch_exp_inplace(slab, nsub * (c1 - c0), c.stream); c.launches += 1; }
-            cuda_check(cudaEventRecord(c.chunk_ev[k], c.stream), "chunk event");
-            cuda_check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[k], 0), "chunk wait");
-            cuda_check(cudaMemcpyAsync(out + c0 * nsub, slab, (size_t)(nsub * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "D2H psi");
-        }
-        cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
-        cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
-        cuda_check(cudaStreamSynchronize(c.copy_stream), "synchronize");
-        return collect(c, code, pair, true);
+        return matrix_host_shard(c, m->m, pop->p, pop->p.view, spp, nspp, np, out, 0, exponentiate, code, pair);
     });
 }
 
@@ -617,6 +761,116 @@ int32_t pharmsol_cuda_psi(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const
     return matrix_host(ctx, m, pop, spp, nspp, np, out, code, pair, true);
 }
 
+// psi resident and REPLICATED on every device of the context (north_star: "psi shards gathered over NVLink"): device k
+// evaluates its block of columns chunk by chunk into its own full matrix and the copy engines push every finished
+// chunk to the other devices while the next chunk is computed (`gather` = PCU_GATHER_COPY_ENGINE), or the psi kernel
+// stores every result straight into all the matrices (PCU_GATHER_PEER_STORES).  dev_out[k] = the library-owned
+// (nsub x nspp) column-major matrix on device k, valid until the next replicated call on this context.
+int32_t pharmsol_cuda_log_likelihood_matrix_replicated(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp,
+                                                       int32_t np, int32_t gather, double** dev_out, int32_t* code, int64_t* pair) {
+    return guarded([&] {
+        if (!ctx || !m || !pop || !spp || !dev_out || nspp < 0 || gather < 0 || gather > 1) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        if (np != (int32_t)m->m.cm.parameters.size())
+            throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
+                                                   " parameter value(s), got " + std::to_string(np));
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        const int n = ctx->ndev();
+        if (n > 8) throw PharmsolError(PCU_ERR_OTHER, "the replicated psi supports at most 8 devices");
+        if ((int)pop->p.replicas.size() + 1 != n) throw PharmsolError(PCU_ERR_OTHER, "population was created for another context (device list differs)");
+        const int64_t nsub = pop->p.flat.nsub;
+        for (int k = 0; k < n; ++k) dev_out[k] = nullptr;
+        if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
+        std::vector<double*> peers((size_t)n);
+        for (int k = 0; k < n; ++k) {
+            Ctx& c = ctx->dev(k);
+            cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+            c.full.reserve((size_t)nsub * nspp * 8);
+            peers[(size_t)k] = c.full.as<double>();
+        }
+        const int64_t per = shard_columns(nspp, n);
+        // phase 1 (concurrent): upload + launches + pushes, all asynchronous on each device's stream
+        int32_t rc = for_each_device(ctx, [&](int k, int32_t*, int64_t*) {
+            Ctx& c = ctx->dev(k);
+            cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+            c.status_batch = false;
+            const int64_t lo = std::min<int64_t>(nspp, k * per), hi = std::min<int64_t>(nspp, lo + per);
+            if (hi <= lo) return (int32_t)PCU_OK;
+            const int64_t ncols = hi - lo;
+            c.spp_rows.reserve((size_t)ncols * np * 8);
+            c.spp_soa.reserve((size_t)ncols * np * 8);
+            cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp + lo * np, (size_t)ncols * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+            launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), ncols, np, ncols, c.stream);
+            c.launches += 1;
+            if (gather == PCU_GATHER_PEER_STORES) {
+                launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), ncols, ncols, nullptr, nsub, nullptr, 0, lo, c.stream, nullptr, true, peers.data(), n,
+                           &pop->p.view_on(k));
+            } else {
+                launch_psi_push(c, m->m, pop->p, pop->p.view_on(k), c.spp_soa.as<double>(), ncols, ncols, peers.data(), n, k, nsub, lo, c.stream);
+            }
+            cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
+            return (int32_t)PCU_OK;
+        }, nullptr, nullptr);
+        // phase 2: every device's stream drained == every matrix complete (each stream ends after its own pushes / stores)
+        int32_t first_code = 0;
+        int64_t first_pair = -1;
+        std::string first_msg;
+        for (int k = 0; k < n; ++k) {
+            Ctx& c = ctx->dev(k);
+            cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+            cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+            const int64_t lo = std::min<int64_t>(nspp, k * per);
+            if (rc != PCU_OK || lo >= nspp) continue;
+            int32_t sc = 0; int64_t sp = -1;
+            if (collect(c, &sc, &sp, true) != PCU_OK && sc != 0 && (first_code == 0 || sp < first_pair)) { first_code = sc; first_pair = sp; first_msg = last_error(); }
+        }
+        cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        if (rc != PCU_OK) return rc;
+        for (int k = 0; k < n; ++k) dev_out[k] = peers[(size_t)k];
+        if (code) *code = first_code;
+        if (pair) *pair = first_pair;
+        if (first_code) set_last_error(first_msg);
+        return first_code;
+    });
+}
+
+// estimate_predictions for one device's block of columns.  The (nobs x ncols) block is produced in column chunks of at
+// most ~256 MB through two device buffers: chunk k is copied back (a strided 2-D copy into the caller's row-major
+// matrix) while chunk k+1 is computed, so a C3-sized grid (10^5 rows x 6,250 columns = 5 GB) needs 0.5 GB of HBM.
+static int32_t predictions_shard(Ctx& c, Model& m, Population& pop, const psi::PopView& view, const double* spp_rows, int64_t ncols, int32_t np,
+                                 double* out, int64_t ld_out, int64_t first_col, int32_t* code, int64_t* pair) {
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    c.status_batch = false;
+    const int64_t nobs = pop.flat.nobs_total;
+    int64_t chunk = std::max<int64_t>(128, ((256ll << 20) / std::max<int64_t>(1, nobs * 8)) / 128 * 128);
+    chunk = std::min<int64_t>(chunk, (ncols + 127) / 128 * 128);
+    c.spp_rows.reserve((size_t)ncols * np * 8);
+    c.spp_soa.reserve((size_t)ncols * np * 8);
+    c.pred.reserve((size_t)nobs * chunk * 8 * 2);
+    cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp_rows, (size_t)ncols * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
+    launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), ncols, np, ncols, c.stream);
+    c.launches += 1;
+    int k = 0;
+    for (int64_t c0 = 0; c0 < ncols; c0 += chunk, ++k) {
+        const int64_t c1 = std::min<int64_t>(ncols, c0 + chunk);
+        double* buf = c.pred.as<double>() + (size_t)(k & 1) * nobs * chunk;
+        // the buffer is free again once the copy issued two chunks ago has finished
+        if (k >= 2) cuda_check(cudaStreamWaitEvent(c.stream, c.chunk_ev[Ctx::kMaxChunks - 1 - (k & 1)], 0), "buffer wait");
+        // predictions need no error model: run with the likelihood output disabled
+        launch_psi(c, m, pop, c.spp_soa.as<double>() + c0, c1 - c0, ncols, nullptr, pop.flat.nsub, buf, chunk, first_col + c0, c.stream, nullptr, k == 0, nullptr, 0, &view);
+        c.status_batch = true;
+        cuda_check(cudaEventRecord(c.chunk_ev[k & 1], c.stream), "chunk event");
+        cuda_check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[k & 1], 0), "chunk wait");
+        cuda_check(cudaMemcpy2DAsync(out + first_col + c0, (size_t)ld_out * 8, buf, (size_t)chunk * 8, (size_t)(c1 - c0) * 8, (size_t)nobs, cudaMemcpyDeviceToHost,
+                                     c.copy_stream), "D2H predictions");
+        cuda_check(cudaEventRecord(c.chunk_ev[Ctx::kMaxChunks - 1 - (k & 1)], c.copy_stream), "copy event");
+    }
+    c.status_batch = false;
+    cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
+    cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
+    cuda_check(cudaStreamSynchronize(c.copy_stream), "synchronize");
+    return collect(c, code, pair, true);
+}
+
 int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, const double* spp, int64_t nspp, int32_t np, double* out) {
     return guarded([&] {
         if (!ctx || !m || !pop || !spp || !out || nspp < 0) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
@@ -624,24 +878,19 @@ int32_t pharmsol_cuda_predictions(pcu_ctx* ctx, pcu_model* m, pcu_population* po
             throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
                                                    " parameter value(s), got " + std::to_string(np));
         std::lock_guard<std::mutex> lk(ctx->c.mu);
-        Ctx& c = ctx->c;
-        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-        c.status_batch = false;
         const int64_t nobs = pop->p.flat.nobs_total;
         if (nspp == 0 || nobs == 0) return (int32_t)PCU_OK;
-        c.spp_rows.reserve((size_t)nspp * np * 8);
-        c.spp_soa.reserve((size_t)nspp * np * 8);
-        c.pred.reserve((size_t)nobs * nspp * 8);
-        cuda_check(cudaMemcpyAsync(c.spp_rows.p, spp, (size_t)nspp * np * 8, cudaMemcpyHostToDevice, c.stream), "H2D support points");
-        launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), nspp, np, nspp, c.stream);
-        c.launches += 1;
-        // predictions need no error model: run with the likelihood output disabled
-        launch_psi(c, m->m, pop->p, c.spp_soa.as<double>(), nspp, nspp, nullptr, pop->p.flat.nsub, c.pred.as<double>(), nspp, 0, c.stream);
-        cuda_check(cudaMemcpyAsync(out, c.pred.p, (size_t)nobs * nspp * 8, cudaMemcpyDeviceToHost, c.stream), "D2H predictions");
-        cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
-        cuda_check(cudaStreamSynchronize(c.stream), "synchronize");
         int32_t code = 0; int64_t pair = -1;
-        return collect(c, &code, &pair, true);
+        if (use_all_devices(ctx, nspp)) {
+            if ((int)pop->p.replicas.size() + 1 != ctx->ndev()) throw PharmsolError(PCU_ERR_OTHER, "population was created for another context (device list differs)");
+            const int64_t per = shard_columns(nspp, ctx->ndev());
+            return for_each_device(ctx, [&](int k, int32_t* scode, int64_t* spair) {
+                const int64_t lo = std::min<int64_t>(nspp, k * per), hi = std::min<int64_t>(nspp, lo + per);
+                if (hi <= lo) return (int32_t)PCU_OK;
+                return predictions_shard(ctx->dev(k), m->m, pop->p, pop->p.view_on(k), spp + lo * np, hi - lo, np, out, nspp, lo, scode, spair);
+            }, &code, &pair);
+        }
+        return predictions_shard(ctx->c, m->m, pop->p, pop->p.view, spp, nspp, np, out, nspp, 0, &code, &pair);
     });
 }
 

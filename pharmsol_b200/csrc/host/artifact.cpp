@@ -15,6 +15,8 @@
 #include <fstream>
 #include <sstream>
 
+#include <cmath>
+
 #include "runtime.hpp"
 
 namespace pharmsol {
@@ -70,6 +72,12 @@ void apply_artifact_settings(const std::string& text, psi::RunOpts& o) {
         else if (k == "em_dt") o.em_dt = std::stod(v);
         else if (k == "cov_time") o.cov_time = std::stoi(v);
     }
+    // the same ranges the pharmsol_cuda_model_set_* entry points enforce: the checksum only detects corruption, a
+    // well-formed file can still carry values no setter would accept
+    const bool ok = o.solver >= 0 && o.solver < psi::SOLVER_COUNT && o.rtol > 0.0 && o.atol > 0.0 && std::isfinite(o.rtol) && std::isfinite(o.atol) &&
+                    o.max_steps > 0 && o.nparticles > 0 && o.sde_mode >= 0 && o.sde_mode <= 1 && o.em_mode >= 0 && o.em_mode <= 1 &&
+                    o.em_dt > 0.0 && std::isfinite(o.em_dt) && o.cov_time >= 0 && o.cov_time <= 1;
+    if (!ok) throw PharmsolError(psi::ST_OTHER, "artifact has invalid settings");
 }
 
 void write_artifact(Model& m, const std::string& path, const std::vector<int>& solvers) {

@@ -24,7 +24,7 @@ int main(int argc, char** argv) {
         auto cm = pharmsol::dsl::compile_source(ss.str());
         if (info) { std::cout << cm.model_info_json() << "\n"; return 0; }
         std::vector<std::pair<int, std::string>> entries;
-        const int nsolvers = cm.kind == pharmsol::dsl::ModelKind::Ode ? 5 : 1;
+        const int nsolvers = cm.kind == pharmsol::dsl::ModelKind::Ode ? 7 : 1;
         for (int s = 0; s < nsolvers; ++s) entries.emplace_back(s, "psi_entry_" + cm.id + "_s" + std::to_string(s));
         std::cout << cm.cuda_source(entries, aot);
     } catch (const std::exception& e) {

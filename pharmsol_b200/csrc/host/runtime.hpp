@@ -51,6 +51,13 @@ struct Ctx {
     double* small_host = nullptr;             // pinned staging for latency-bound calls: [0, kSmallIn) support points SoA, then psi
     static constexpr size_t kSmallIn = 64u << 10, kSmallOut = 256u << 10;
     DevBuf spp_rows, spp_soa, out, pred, scratch;
+    // device-resident, replicated psi of a multi-device context (pharmsol_cuda_log_likelihood_matrix_replicated) and the
+    // streams / events of the copy-engine push gather: finished column chunks are pushed to the peers over NVLink by
+    // cudaMemcpyAsync on these streams while the next chunk is computed
+    DevBuf full;
+    static constexpr int kPeerStreams = 4;
+    cudaStream_t peer_streams[kPeerStreams] = {};
+    cudaEvent_t peer_ev[kPeerStreams] = {};
     DevBuf col_work, col_idx, col_sort;      // work-balanced column order (ODE): probe counts, permutation, cub scratch
     int64_t launches = 0;
     bool status_batch = false;                // several launches share one error word / counter set until the next collect
@@ -72,6 +79,12 @@ struct Model {
     std::mutex mu;
 };
 
+// The flattened population on one more device of a multi-device context (the primary copy lives in Population itself).
+struct PopReplica {
+    int device = 0;
+    DevBuf dev;
+    psi::PopView view{};
+};
 struct Population {
     Data data;
     ModelLabels labels;
@@ -79,7 +92,11 @@ struct Population {
     DevBuf dev;
     psi::PopView view{};
     int device = 0;
-    void upload();
+    std::vector<std::unique_ptr<PopReplica>> replicas;      // devices 1.. of the creating context, in context order
+    void upload();                                            // primary device + every replica
+    void upload_into(DevBuf& dev, psi::PopView& view) const;  // current device
+    const psi::PopView& view_on(int ctx_index) const { return ctx_index == 0 ? view : replicas[(size_t)ctx_index - 1]->view; }
+    ~Population();
 };
 
 // --- module management --------------------------------------------------------------------------------
@@ -109,7 +126,17 @@ int effective_solver(const Model& m);
 // --- launches -------------------------------------------------------------------------------------------
 void launch_psi(Ctx& ctx, Model& m, Population& pop, const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
                 double* out_dev, int64_t ld_out, double* pred_dev, int64_t ld_pred, int64_t first_col, cudaStream_t stream,
-                const psi::RunOpts* opts_override = nullptr, bool reset_status = true, double* const* peers = nullptr, int npeers = 0);
+                const psi::RunOpts* opts_override = nullptr, bool reset_status = true, double* const* peers = nullptr, int npeers = 0,
+                const psi::PopView* view = nullptr);
+// Column chunks of one shard for pipelining (copy-back or peer push behind the compute): closed-form models up to
+// `max_chunks` equal chunks of >= 2 MB and >= 128 columns; adaptive ODE / SDE models 7/8 + 1/8 (every extra launch costs
+// a probe + sort of the work-balanced column order and a kernel tail).  Returns the cut points, first 0, last ncols.
+std::vector<int64_t> column_chunks(const Model& m, int64_t nsub, int64_t ncols, int max_chunks);
+// Copy-engine push gather: evaluate [first_col, first_col + ncols) chunk by chunk into peers[self] (a FULL column-major
+// matrix) and push every finished chunk to the other peers with device-to-device copies on the context's peer streams;
+// `stream` ends up ordered after the last push.
+void launch_psi_push(Ctx& ctx, Model& m, Population& pop, const psi::PopView& view, const double* spp_soa_dev, int64_t ncols, int64_t ld_spp,
+                     double* const* peers, int npeers, int self, int64_t ld_out, int64_t first_col, cudaStream_t stream);
 void launch_transpose(const double* rows, double* soa, int64_t nspp, int nparams, int64_t ld, cudaStream_t stream);
 void launch_exp_inplace(double* p, int64_t n, cudaStream_t stream);
 double measure_fp64_peak(Ctx& ctx, double* clock_mhz);

@@ -15,7 +15,6 @@ from benches import harness as H, workloads as W
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-os.environ["NCCL_DEBUG"] = "WARN"
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 for name, nsub, nspp, kw in [("c1", 40, 1003, {}), ("c2", 64, 2500, dict(solver=ps.OdeSolver.Dopri5, tol=1e-6)), ("c3", 16, 777, {}),
@@ -28,15 +27,16 @@ for name, nsub, nspp, kw in [("c1", 40, 1003, {}), ("c2", 64, 2500, dict(solver=
         eq.with_particles(kw["particles"]).with_mode(ps.SdeMode.ParticleFilter).with_seed(99)
     ref = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)          # whole matrix on this GPU, host API
     # fused peer stores | one NCCL all-gather | phased: 7/8 of the columns gathered while the last 1/8 computes
-    for peer, overlap in ((True, False), (False, False), (False, True)):
-        job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=peer, gather_overlap=overlap)
+    for peer, overlap, gmode in ((True, False, "auto"), (False, False, "auto"), (False, True, "auto"), (True, False, "push")):
+        job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, peer_stores=("auto" if gmode == "push" else peer), gather_overlap=overlap, gather=gmode)
         fused = getattr(job.sharded, "peer_ptrs", None) is not None
+        ok = ok and (gmode != "push" or job.gather_mode == "push")
         for _ in range(2):      # twice: the second step runs over the first one's status / buffers
             job.step()
         psi = job.finish().cpu().numpy()
         same = np.array_equal(psi, ref, equal_nan=True)
         ok = ok and same and (fused == peer) and (len(job.ranges) == (2 if overlap else 1))
-        print(f"rank {rank} {name} peer_stores={peer} overlap={overlap} fused={fused} equal_to_single_gpu={same} err={getattr(job.sharded, 'peer_error', None)}", flush=True)
+        print(f"rank {rank} {name} gather={job.gather_mode} peer_stores={peer} overlap={overlap} fused={fused} equal_to_single_gpu={same} err={getattr(job.sharded, 'peer_error', None)}", flush=True)
         dist.barrier()
 # first error propagates to every rank with its global pair index
 eq = ps.Equation.from_dsl("name = twocpt\nkind = analytical\nparams = ke, kcp, kpc, v\nstates = central, peripheral\noutputs = cp\nbolus(iv) -> central\n"

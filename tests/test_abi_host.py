@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(libpath):
     assert not missing, missing
     # and the binding table covers the header exactly
     assert sorted(_lib.lib()._signatures) == declared
-    assert L.pharmsol_cuda_abi_version() == 1
+    assert L.pharmsol_cuda_abi_version() == 2
 
 
 def test_no_torch_types_in_header():

@@ -118,14 +118,14 @@ def test_corpus_analytical(ps, oracle, case):
 
 
 @pytest.mark.parametrize("case", ["ode", "ode_full"])
-@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4"])
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4", "Bdf", "Esdirk34"])
 def test_corpus_ode(ps, oracle, case, solver):
     src, twin, p, ops, _ = FX.CORPUS[case]
     tol = 1e-8 if solver == "TrBdf2" else 1e-10
     eq = ps.Equation.from_dsl(src).with_solver(getattr(ps.OdeSolver, solver)).with_tolerances(tol, tol)
     got = gpu_predictions(ps, eq, ops, p)
     want = oracle.Model(twin, solver="dopri5", rtol=1e-12, atol=1e-12).predictions(oracle.Subject(ops), p)
-    assert rel(got, want, 1e-8).max() <= (1e-5 if solver == "TrBdf2" else 1e-6)   # reference's own bar: 1e-4
+    assert rel(got, want, 1e-8).max() <= (1e-5 if solver in ("TrBdf2", "Bdf") else 1e-6)   # reference's own bar: 1e-4
 
 
 def test_corpus_sde_zero_diffusion_is_deterministic(ps, oracle):
@@ -207,7 +207,8 @@ def test_c2_reference_default_tolerance_agrees_with_oracle_solver(ps, oracle, H,
     assert rel(pred[:offs[1]], want, 1e-3).max() <= 5e-3
 
 
-@pytest.mark.parametrize("solver,tol,bar", [("Sdirk4", 1e-9, 1e-6), ("TrBdf2", 1e-8, 2e-5), ("Dopri5", 1e-10, 1e-6), ("Rodas4", 1e-9, 1e-6)])
+@pytest.mark.parametrize("solver,tol,bar", [("Sdirk4", 1e-9, 1e-6), ("TrBdf2", 1e-8, 2e-5), ("Dopri5", 1e-10, 1e-6), ("Rodas4", 1e-9, 1e-6),
+                                            ("Bdf", 1e-10, 1e-5), ("Esdirk34", 1e-10, 1e-6)])
 def test_c4_stiff_vs_radau_golden(ps, solver, tol, bar):
     """stiff_c4.json: SciPy Radau rtol=1e-12 predictions (ke0 up to 50 /h)."""
     from benches import workloads
@@ -307,7 +308,7 @@ def test_lag_reorders_events_per_support_point(ps, oracle):
     assert rel(pred, want, 1e-10).max() <= 1e-12
 
 
-@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4"])
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Sdirk4", "TrBdf2", "Rodas4", "Bdf", "Esdirk34"])
 def test_ode_infusion_dose_conservation(ps, solver):
     """ode/mod.rs:1274-1344."""
     src = "name = acc\nkind = ode\nparams = ke, v\nstates = central\noutputs = cp\ninfusion(iv) -> central\ndx(central) = -ke * central\nout(cp) = central / v ~ continuous()\n"
@@ -882,7 +883,7 @@ def test_stiff_hybrid_phage_model_vs_radau_golden(ps, solver, tol, bar):
     assert err.max() <= bar, (solver, err.max(), int(err.argmax()))
 
 
-@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Rodas4", "Sdirk4", "TrBdf2"])
+@pytest.mark.parametrize("solver", ["Dopri5", "Tsit45", "Rodas4", "Sdirk4", "TrBdf2", "Bdf", "Esdirk34"])
 def test_ode_event_times_within_ulps_of_boundaries(ps, solver):
     """ode/mod.rs:1347-1455: (1) an infusion that ends one ULP after an observation — the loop must keep integrating to the
     next observation (expected value in closed form); (2) observations 16 ULPs on either side of a bolus time must not
@@ -902,7 +903,7 @@ def test_ode_event_times_within_ulps_of_boundaries(ps, solver):
     got = gpu_predictions(ps, eq2, ops, [0.3])
     assert len(got) == 4 and np.all(np.isfinite(got))
     before = 200.0 * math.exp(-0.3 * 12.0)
-    bar = 2e-5 if solver == "TrBdf2" else 1e-6          # TR-BDF2 is second order: ~5e-6 at tol 1e-8
+    bar = 2e-5 if solver in ("TrBdf2", "Bdf", "Esdirk34") else 1e-6          # TR-BDF2 is second order: ~5e-6 at tol 1e-8
     assert got[0] == 0.0 and got[1] == pytest.approx(before, rel=bar) and got[2] == pytest.approx(before + 100.0, rel=bar)
     assert got[3] == pytest.approx((before + 100.0) * math.exp(-0.3 * 12.0), rel=bar)
 
