@@ -97,7 +97,11 @@ PSI_DEV double block_sum(double v, double* smem4) {
 // sqrt(dt) does not need the last bits; a full FP64 sqrt is ~25 instructions on the bound pipe)
 PSI_DEV double sqrt_fast(double x) {
     double r;
+#ifdef PSI_HOST_SIM
+    r = 1.0 / sqrt(x);
+#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     const double hx = 0.5 * x;
     r = fma(r, fma(-hx * r, r, 0.5), r);       // r <- r (1.5 - 0.5 x r^2)
     r = fma(r, fma(-hx * r, r, 0.5), r);

@@ -1,0 +1,86 @@
+"""CPU checks of the DEVICE SOURCE (csrc/device/*.cuh + the emitted model code) compiled for the host through
+tests/hostsim/cuda_shim.h, against the oracle and the committed goldens.  Test infrastructure: these tests say the
+per-pair logic is right before a GPU runs it; the parity tests proper are the `-m gpu` ones through the C ABI."""
+import numpy as np
+import pytest
+
+import fixtures as FX
+from conftest import golden
+
+
+@pytest.fixture(scope="module")
+def HS():
+    from hostsim import HostSim
+    return HostSim
+
+
+def _ems(w):
+    return [(1 if k == "additive" else 2, f, p) for _, (k, f, p) in w["error_models"].items()]
+
+
+def _scaled(a, b, nobs):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + nobs)))
+
+
+def test_c1_and_c3_closed_forms_match_the_oracle(HS, oracle):
+    from benches import harness as H, workloads as W
+    for name, bar, nobs, mode in (("c1", 1e-12, 10, None), ("c3", 1e-10, 10, "interval_end"), ("c3", 1e-10, 10, "interval_length")):
+        w = W.make(name, nsub=5, nspp=40)
+        if mode:
+            w["oracle_model"] = "c3_three_cpt_cov_" + mode
+        hs = HS(w["dsl"]).set_subjects(w["subjects"])
+        psi, pred, info = hs.run(w["support_points"], _ems(w), cov_time=1 if mode == "interval_length" else 0, want_pred=True)
+        om, od, oe = H.oracle_objects(w)
+        ref = om.log_likelihood_matrix(od, w["support_points"], oe)
+        assert info["code"] == 0 and _scaled(psi, ref, nobs) <= bar
+        want = np.array([om.predictions(od.subjects[2], s) for s in w["support_points"][:6]]).T
+        lo = 2 * nobs
+        assert np.max(np.abs(pred[lo:lo + nobs, :6] - want) / np.maximum(np.abs(want), 1e-10)) <= bar * 10
+
+
+@pytest.mark.parametrize("solver,tol,bar", [("Dopri5", 1e-10, 1e-6), ("Tsit45", 1e-10, 1e-6), ("Sdirk4", 1e-9, 1e-6), ("TrBdf2", 1e-8, 2e-5),
+                                            ("Rodas4", 1e-9, 1e-6), ("Bdf", 1e-10, 1e-6), ("Esdirk34", 1e-10, 1e-6)])
+def test_c2_every_solver_against_the_closed_form(HS, oracle, solver, tol, bar):
+    """ode/mod.rs:59-84: all of the reference's solver names (Bdf, TrBdf2, Esdirk34, Tsit45) plus this backend's own."""
+    from benches import harness as H, workloads as W
+    w = W.make("c2", nsub=4, nspp=16)
+    hs = HS(w["dsl"]).set_subjects(w["subjects"])
+    psi, _, info = hs.run(w["support_points"], _ems(w), solver=solver, rtol=tol, atol=tol)
+    om, od, oe = H.oracle_objects(dict(w, oracle_model=w["oracle_truth_model"]))
+    ref = om.log_likelihood_matrix(od, w["support_points"], oe)
+    assert info["code"] == 0 and _scaled(psi, ref, 12) <= bar, (solver, _scaled(psi, ref, 12))
+
+
+@pytest.mark.parametrize("solver,tol,bar", [("Bdf", 1e-10, 1e-6), ("Bdf", 1e-6, 1e-4), ("Esdirk34", 1e-10, 1e-6), ("Rodas4", 1e-9, 1e-6)])
+def test_stiff_model_against_radau_goldens(HS, solver, tol, bar):
+    from benches import workloads as W
+    hs = HS(W.model_source("c4_mm_effect"))
+    for c in golden("stiff_c4"):
+        hs.set_subjects([("s", [tuple(o) for o in c["ops"]])])
+        _, pred, info = hs.run(np.array([c["params"]]), None, solver=solver, rtol=tol, atol=tol, want_pred=True)
+        want = np.array(c["predictions"])
+        assert info["code"] == 0
+        assert np.max(np.abs(pred[:, 0] - want) / np.maximum(np.abs(want), 1e-6)) <= bar, (solver, c["params"])
+
+
+def test_bdf_work_is_bounded_and_orders_climb(HS):
+    """The multistep method must actually use its history: at rtol = 1e-8 on a smooth decay a first-order method would
+    need ~1e4 steps per unit time; the variable-order scheme needs a few hundred."""
+    src = "name = decay\nkind = ode\nparams = k\nstates = central\noutputs = cp\nbolus(iv) -> central\ndx(central) = -k * central\nout(cp) = central ~ continuous()\n"
+    hs = HS(src).set_subjects([("s", [("bolus", 0.0, 100.0, "iv"), ("missing_observation", 10.0, "cp")])])
+    _, pred, info = hs.run(np.array([[0.3]]), None, solver="Bdf", rtol=1e-8, atol=1e-8, want_pred=True)
+    assert abs(pred[0, 0] - 100.0 * np.exp(-3.0)) <= 1e-5
+    assert info["steps"] < 600, info
+
+
+def test_esdirk34_observed_order_is_three(HS):
+    """Fixed-step convergence of the advancing method on y' = -y + sin t (forced through h0 with loose tolerances is not
+    available, so measure the global error at two tolerances two decades apart: error ratio ~ 100^(3/4))."""
+    src = "name = forced\nkind = ode\nparams = k\nstates = y\noutputs = o\nbolus(iv) -> y\ndx(y) = -k * y + sin(t)\nout(o) = y ~ continuous()\n"
+    hs = HS(src).set_subjects([("s", [("bolus", 0.0, 1.0, "iv"), ("missing_observation", 4.0, "o")])])
+    exact = (lambda t: 1.5 * np.exp(-t) + 0.5 * (np.sin(t) - np.cos(t)))(4.0)
+    errs = []
+    for tol in (1e-5, 1e-7, 1e-9):
+        _, pred, info = hs.run(np.array([[1.0]]), None, solver="Esdirk34", rtol=tol, atol=tol, want_pred=True)
+        errs.append(abs(pred[0, 0] - exact))
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-7
