@@ -113,9 +113,86 @@ static int run_case(pcu_ctx* ctx, const char* label, const char* dsl, int repeat
     return 0;
 }
 
-int main(void) {
+/* --devices a,b,...: the same call through a MULTI-DEVICE context (pharmsol_cuda_ctx_create_multi): the library splits
+ * the support-point columns over the listed devices inside this one process and every device copies its slab straight
+ * into the caller's matrix.  A larger case than the criterion shapes (256 subjects x `nspp` support points of the
+ * 2-compartment ODE) is evaluated on device list[0] alone and on the whole list; the two matrices must be identical
+ * bit for bit.  A device may be listed twice (two column shards on one GPU). */
+static int run_multi(const int32_t* devs, int ndev, int64_t nspp) {
+    enum { NS = 256 };
+    pcu_ctx *one = NULL, *many = NULL;
+    CHECK(pharmsol_cuda_ctx_create(devs[0], &one));
+    CHECK(pharmsol_cuda_ctx_create_multi(devs, ndev, &many));
+    pcu_model* m = NULL;
+    CHECK(pharmsol_cuda_model_from_dsl(one, kRepeatOde, strlen(kRepeatOde), &m));
+    CHECK(pharmsol_cuda_model_set_solver(m, PCU_SOLVER_DOPRI5, 1e-6, 1e-6));
+    pcu_data* d = pharmsol_data_new();
+    for (int i = 0; i < NS; ++i) {
+        char id[32];
+        snprintf(id, sizeof id, "multi-%03d", i);
+        pcu_subject_builder* b = pharmsol_subject_builder_new(id);
+        for (int k = 0; k < 10; ++k) pharmsol_subject_builder_bolus(b, 12.0 * k, 100.0 + 0.1 * i, "iv");
+        for (int k = 0; k < 14; ++k) pharmsol_subject_builder_observation(b, kRepeatT[k], kRepeatY[k] + i * 0.001, "plasma");
+        pcu_subject* s = pharmsol_subject_builder_build(b);
+        pharmsol_data_add_subject(d, s);
+        pharmsol_subject_free(s);
+    }
+    pcu_error_model em;
+    memset(&em, 0, sizeof em);
+    em.kind = PCU_ERRMODEL_ADDITIVE; em.c0 = 0.1; em.c1 = 0.1;
+    pcu_population *pop1 = NULL, *popn = NULL;
+    CHECK(pharmsol_cuda_population_create(one, m, d, &em, 1, &pop1));
+    CHECK(pharmsol_cuda_population_create(many, m, d, &em, 1, &popn));
+    double* spp = malloc((size_t)nspp * 4 * sizeof(double));      /* pageable, like a caller's own arrays */
+    double* a = malloc((size_t)NS * nspp * sizeof(double));
+    double* b2 = malloc((size_t)NS * nspp * sizeof(double));
+    if (!spp || !a || !b2) return 1;
+    const double base[4] = {0.10, 0.05, 0.04, 50.0};
+    for (int64_t r = 0; r < nspp; ++r)
+        for (int k = 0; k < 4; ++k) spp[r * 4 + k] = base[k] * (1.0 + 0.9 * (double)((r * 2654435761u + k * 40503u) % 1000) / 1000.0);
+    int32_t code = 0; int64_t pair = -1;
+    double t1 = 1e30, tn = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        double t0 = now_s();
+        CHECK(pharmsol_cuda_log_likelihood_matrix(one, m, pop1, spp, nspp, 4, a, &code, &pair));
+        if (rep && now_s() - t0 < t1) t1 = now_s() - t0;
+        t0 = now_s();
+        CHECK(pharmsol_cuda_log_likelihood_matrix(many, m, popn, spp, nspp, 4, b2, &code, &pair));
+        if (rep && now_s() - t0 < tn) tn = now_s() - t0;
+    }
+    const int same = memcmp(a, b2, (size_t)NS * nspp * sizeof(double)) == 0;
+    /* the whole psi resident on every device, gathered over NVLink by the copy engines */
+    double* dev_out[64];
+    double t0 = now_s();
+    CHECK(pharmsol_cuda_log_likelihood_matrix_replicated(many, m, popn, spp, nspp, 4, PCU_GATHER_COPY_ENGINE, dev_out, &code, &pair));
+    const double trep = now_s() - t0;
+    int all_ptrs = 1;
+    for (int k = 0; k < ndev; ++k) all_ptrs = all_ptrs && dev_out[k] != NULL;
+    printf("{\"bench\": \"native/likelihood-matrix/multi-device\", \"caller\": \"C\", \"devices\": %d, \"nsub\": %d, \"nspp\": %lld, "
+           "\"ms_single_device\": %.4f, \"ms_multi_device\": %.4f, \"ms_replicated\": %.4f, \"matches_single_device\": %s, \"replicated_ptrs\": %s, "
+           "\"first_error_code\": %d, \"launches\": %lld}\n",
+           pharmsol_cuda_ctx_num_devices(many), NS, (long long)nspp, t1 * 1e3, tn * 1e3, trep * 1e3, same ? "true" : "false", all_ptrs ? "true" : "false", (int)code,
+           (long long)pharmsol_cuda_launch_count(many));
+    free(spp); free(a); free(b2);
+    pharmsol_cuda_population_destroy(pop1);
+    pharmsol_cuda_population_destroy(popn);
+    pharmsol_data_free(d);
+    pharmsol_cuda_model_destroy(m);
+    pharmsol_cuda_ctx_destroy(many);
+    pharmsol_cuda_ctx_destroy(one);
+    return same && all_ptrs ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
     int32_t ndev = 0;
     if (pharmsol_cuda_device_count(&ndev) != PCU_OK || ndev < 1) { fprintf(stderr, "no CUDA device: %s\n", pharmsol_cuda_last_error_message()); return 2; }
+    if (argc >= 3 && strcmp(argv[1], "--devices") == 0) {
+        int32_t devs[64];
+        int n = 0;
+        for (char* tok = strtok(argv[2], ","); tok && n < 64; tok = strtok(NULL, ",")) devs[n++] = (int32_t)atoi(tok);
+        const int64_t nspp = argc >= 4 ? atoll(argv[3]) : 8192;
+        return n > 0 ? run_multi(devs, n, nspp) : 2;
+    }
     pcu_ctx* ctx = NULL;
     CHECK(pharmsol_cuda_ctx_create(0, &ctx));
     int rc = 0;

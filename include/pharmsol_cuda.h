@@ -207,6 +207,22 @@ int32_t pharmsol_cuda_model_load_artifact(pcu_ctx* ctx, const char* path, pcu_mo
  * byte count needed (excluding the terminator), -1 on error; writes at most cap - 1 bytes + NUL into buf. */
 int64_t pharmsol_cuda_artifact_info_json(const char* path, char* buf, size_t cap);
 
+/* ---- native (host) artifact with the reference's frozen compiled-backend ABI ---------------------------------------
+ * SURVEY §8 f.2 as written: a cdylib that the reference's own `load_aot_model` (src/dsl/aot.rs:316-353) can open. The
+ * DSL emitter writes the HOST twin of the model it emits for the device — the same function bodies, C++ instead of CUDA
+ * C — exporting the frozen symbols of src/dsl/compiled_backend_abi.rs:6-33:
+ *     uint32_t pharmsol_dsl_api_version(void)                    == AOT_API_VERSION = 2 (aot.rs:43, 404-417)
+ *     const uint8_t* pharmsol_dsl_model_info_json_ptr(void), size_t pharmsol_dsl_model_info_json_len(void)
+ *                                                                 CompiledModelInfoEnvelope{abi_version, model, functions}
+ *     void pharmsol_dsl_kernel_{outputs,derive,dynamics,init,drift,diffusion,route_lag,route_bioavailability}
+ *          (double t, const double* states, const double* params, const double* covariates, const double* routes,
+ *           const double* derived, double* out)                   CompiledModelFunction, dsl/native.rs:45-53
+ * (only the roles the model has; `outputs` always).  `*_host_source` returns the generated C++ translation unit (owned
+ * by the model); `*_export_host_artifact` compiles it with the system C++ compiler ($PHARMSOL_B200_CXX, default g++) the
+ * way the reference shells out to cargo.  No GPU is involved. */
+const char* pharmsol_cuda_model_host_source(pcu_model* m);
+int32_t pharmsol_cuda_model_export_host_artifact(pcu_model* m, const char* path);
+
 /* ---- population: flattened Data resident in HBM ------------------------------------------------------ */
 /* Resolve labels against the model's routes / outputs (equation/mod.rs:192-273, dsl/native.rs:663-770),
  * precompute the per-observation sigma terms from `error_models` (may be NULL for predictions only),

@@ -10,7 +10,7 @@ from ._lib import PharmsolError, LIB_PATH, device_count  # noqa: F401
 from .api import (  # noqa: F401
     Analytical, AssayErrorModel, AssayErrorModels, Censor, CovTime, Data, EmMode, EqnKind, Equation, ErrorPoly, ODE, OdeSolver,
     ParameterOrder, Prediction, ResidentPsi, ResidualErrorModel, ResidualErrorModels, SDE, SdeMode, Subject, SubjectBuilder, SubjectPredictions, RuntimeArtifactFormat, RuntimeBackend, RuntimeCompilationTarget, analytical,
-    compile_module_source_to_aot, compile_module_source_to_runtime, load_aot_model, load_runtime_artifact, read_aot_model_info, log_likelihood_batch, log_likelihood_matrix, log_psi, ode, psi, read_pmetrics, sde,
+    NativeArtifact, compile_module_source_to_native_aot, compile_module_source_to_aot, compile_module_source_to_runtime, load_aot_model, load_runtime_artifact, read_aot_model_info, log_likelihood_batch, log_likelihood_matrix, log_psi, ode, psi, read_pmetrics, sde,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

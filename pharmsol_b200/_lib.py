@@ -138,6 +138,8 @@ def lib():
         "pharmsol_cuda_log_likelihood_batch": (i32, [vp, vp, vp, dp, i64, i32, P(pcu_residual_error_model), i32, dp]),
         "pharmsol_cuda_measure_fp64_peak": (i32, [vp, dp, dp]),
         "pharmsol_cuda_model_export_artifact": (i32, [vp, C.c_char_p, P(i32), i32]),
+        "pharmsol_cuda_model_host_source": (cs, [vp]),
+        "pharmsol_cuda_model_export_host_artifact": (i32, [vp, C.c_char_p]),
         "pharmsol_cuda_model_load_artifact": (i32, [vp, C.c_char_p, P(vp)]),
         "pharmsol_cuda_artifact_info_json": (i64, [C.c_char_p, C.c_char_p, C.c_size_t]),
     }
@@ -389,6 +391,15 @@ class Model:
     def export_artifact(self, path, solvers=()):
         arr = (C.c_int32 * max(len(solvers), 1))(*[int(s) for s in solvers])
         check(lib().pharmsol_cuda_model_export_artifact(self.ptr, str(path).encode(), arr, len(solvers)))
+        return str(path)
+
+    @property
+    def host_source(self):
+        """C++ source of the host twin exporting the reference's frozen compiled-backend symbols."""
+        return lib().pharmsol_cuda_model_host_source(self.ptr).decode()
+
+    def export_host_artifact(self, path):
+        check(lib().pharmsol_cuda_model_export_host_artifact(self.ptr, str(path).encode()))
         return str(path)
 
     @classmethod

@@ -618,6 +618,56 @@ def compile_module_source_to_aot(source, output, solvers=(), configure=None):
     return eq.export_artifact(output, solvers)
 
 
+def compile_module_source_to_native_aot(source, output):
+    """dsl/aot.rs:146-300 for the HOST target: DSL source -> a cdylib exporting the reference's frozen compiled-backend
+    symbols (`pharmsol_dsl_api_version`, `pharmsol_dsl_model_info_json_{ptr,len}`, `pharmsol_dsl_kernel_*`), i.e. a
+    `.pkm` the reference's own `load_aot_model` opens.  The emitter writes the host twin of the device code; the system
+    C++ compiler builds it.  Returns the output path."""
+    return Equation.from_dsl(source)._model.export_host_artifact(output)
+
+
+class NativeArtifact:
+    """A loaded host artifact (what `load_aot_model` does with libloading, dsl/aot.rs:316-353, 404-470): version check,
+    model-info envelope, the role functions as callables `(t, states, params, covariates, routes, derived, out_len) -> out`."""
+    ROLES = ("derive", "dynamics", "outputs", "init", "drift", "diffusion", "route_lag", "route_bioavailability")
+
+    def __init__(self, path):
+        import ctypes as C
+        import json
+        self._lib = C.CDLL(str(path))
+        ver = self._lib.pharmsol_dsl_api_version
+        ver.restype = C.c_uint32
+        if ver() != 2:
+            raise PharmsolError(15, f"artifact API version {ver()} != 2")
+        ptr, ln = self._lib.pharmsol_dsl_model_info_json_ptr, self._lib.pharmsol_dsl_model_info_json_len
+        ptr.restype, ln.restype = C.c_void_p, C.c_size_t
+        self.envelope = json.loads(C.string_at(ptr(), ln()).decode())
+        self.info = self.envelope["model"]
+        self.functions = {}
+        dp = C.POINTER(C.c_double)
+        for role in self.ROLES:
+            try:
+                fn = getattr(self._lib, "pharmsol_dsl_kernel_" + role)
+            except AttributeError:
+                continue
+            fn.restype = None
+            fn.argtypes = [C.c_double, dp, dp, dp, dp, dp, dp]
+            self.functions[role] = fn
+        if "outputs" not in self.functions:
+            raise PharmsolError(15, "artifact lacks the required symbol pharmsol_dsl_kernel_outputs")
+
+    def call(self, role, t, states, params, covariates=(), routes=(), derived=(), out=None, out_len=None):
+        import ctypes as C
+        dp = C.POINTER(C.c_double)
+        arr = lambda v, n=1: np.ascontiguousarray(list(v) + [0.0] * max(0, n - len(v)), dtype=np.float64)
+        st, pr, cv, rt, dv = arr(states), arr(params), arr(covariates), arr(routes), arr(derived)
+        if out is None:
+            out = np.zeros(max(int(out_len or 1), 1))
+        ptr = lambda a: a.ctypes.data_as(dp)
+        self.functions[role](float(t), ptr(st), ptr(pr), ptr(cv), ptr(rt), ptr(dv), ptr(out))
+        return out
+
+
 def load_aot_model(path, device=None):
     """dsl/aot.rs:316-353"""
     return Equation.from_artifact(path, device)

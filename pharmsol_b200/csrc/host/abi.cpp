@@ -393,6 +393,45 @@ int64_t pharmsol_cuda_artifact_info_json(const char* path, char* buf, size_t cap
     });
     return need;
 }
+// ---- native (host) artifact with the reference's frozen symbols --------------------------------------------------
+const char* pharmsol_cuda_model_host_source(pcu_model* m) {
+    if (!m) return "";
+    std::lock_guard<std::mutex> lk(m->m.mu);
+    try {
+        if (m->m.host_source_cache.empty()) m->m.host_source_cache = m->m.cm.host_source();
+    } catch (const std::exception& e) { set_last_error(e.what()); return ""; }
+    return m->m.host_source_cache.c_str();
+}
+int32_t pharmsol_cuda_model_export_host_artifact(pcu_model* m, const char* path) {
+    return guarded([&] {
+        if (!m || !path) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
+        const std::string src = m->m.cm.host_source();
+        const std::string out = path;
+        const std::string tmp_src = out + ".src." + std::to_string((long long)::getpid()) + ".cpp";
+        const std::string tmp_out = out + ".tmp." + std::to_string((long long)::getpid());
+        const std::string log = out + ".log." + std::to_string((long long)::getpid());
+        {
+            FILE* f = std::fopen(tmp_src.c_str(), "wb");
+            if (!f) throw PharmsolError(PCU_ERR_OTHER, "cannot write " + tmp_src);
+            std::fwrite(src.data(), 1, src.size(), f);
+            std::fclose(f);
+        }
+        // the reference shells out to `cargo build` for its cdylib (dsl/aot.rs:146-300); the host twin is C++, so the
+        // system C++ compiler plays that part ($PHARMSOL_B200_CXX, else $CXX, else g++)
+        const char* cxx = std::getenv("PHARMSOL_B200_CXX");
+        if (!cxx || !*cxx) cxx = "g++";
+        auto quote = [](const std::string& a) { std::string q = "'"; for (char ch : a) { if (ch == '\'') q += "'\\''"; else q += ch; } return q + "'"; };
+        const std::string cmd = quote(cxx) + " -std=c++17 -O2 -fPIC -shared -fvisibility=default -ffp-contract=off -o " + quote(tmp_out) + " " + quote(tmp_src) + " > " + quote(log) + " 2>&1";
+        const int rc = std::system(cmd.c_str());
+        std::string text;
+        if (FILE* f = std::fopen(log.c_str(), "rb")) { char buf[4096]; size_t n; while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n); std::fclose(f); }
+        std::remove(log.c_str());
+        std::remove(tmp_src.c_str());
+        if (rc != 0) { std::remove(tmp_out.c_str()); throw dsl::DslError("host compiler failed for the native artifact (" + std::string(cxx) + "):\n" + text); }
+        if (std::rename(tmp_out.c_str(), out.c_str()) != 0) { std::remove(tmp_out.c_str()); throw PharmsolError(PCU_ERR_OTHER, "cannot write " + out); }
+        return (int32_t)PCU_OK;
+    });
+}
 void pharmsol_cuda_model_destroy(pcu_model* m) { delete m; }
 int32_t pharmsol_cuda_model_kind(const pcu_model* m) { return m ? (int32_t)m->m.cm.kind : -1; }
 int32_t pharmsol_cuda_model_nparams(const pcu_model* m) { return m ? (int32_t)m->m.cm.parameters.size() : -1; }
@@ -634,14 +673,22 @@ static int32_t matrix_host_shard(Ctx& c, Model& m, Population& pop, const psi::P
     launch_transpose(c.spp_rows.as<double>(), c.spp_soa.as<double>(), ncols, np, ncols, c.stream);
     c.launches += 1;
     const std::vector<int64_t> cuts = column_chunks(m, nsub, ncols, Ctx::kMaxChunks);
+    // All the launches are queued first and the copies second: a copy into PAGEABLE caller memory (a Rust Array2, a
+    // numpy array) blocks the issuing thread until it is done, and issued chunk by chunk in one loop it would serialise
+    // with the launches (C3 shard: 63 ms = 32 ms kernels + 31 ms copies; queued this way the copies of the early chunks
+    // run under the kernels of the later ones).  For pinned buffers the order makes no difference.
     for (size_t k = 0; k + 1 < cuts.size(); ++k) {
         const int64_t c0 = cuts[k], c1 = cuts[k + 1];
         double* slab = c.out.as<double>() + c0 * nsub;
         launch_psi(c, m, pop, c.spp_soa.as<double>() + c0, c1 - c0, ncols, slab, nsub, nullptr, 0, first_col + c0, c.stream, nullptr, k == 0, nullptr, 0, &view);
         if (exponentiate) { launch_exp_inplace(slab, nsub * (c1 - c0), c.stream); c.launches += 1; }
         cuda_check(cudaEventRecord(c.chunk_ev[k], c.stream), "chunk event");
+    }
+    cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int64_t c0 = cuts[k], c1 = cuts[k + 1];
         cuda_check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[k], 0), "chunk wait");
-        cuda_check(cudaMemcpyAsync(out + c0 * nsub, slab, (size_t)(nsub * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "D2H psi");
+        cuda_check(cudaMemcpyAsync(out + c0 * nsub, c.out.as<double>() + c0 * nsub, (size_t)(nsub * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, c.copy_stream), "D2H psi");
     }
     cuda_check(cudaMemcpyAsync(c.err_host, c.err_ctr.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), "D2H status");
     cuda_check(cudaStreamSynchronize(c.stream), "synchronize");

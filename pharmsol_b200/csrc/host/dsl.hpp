@@ -108,6 +108,9 @@ struct CompiledModel {
     // Full translation unit.  `entries`: list of (solver, entry symbol) to instantiate.
     std::string cuda_source(const std::vector<std::pair<int, std::string>>& entries, bool aot_register) const;
     std::string model_info_json() const;
+    // Host twin exporting the reference's frozen compiled-backend ABI (compiled_backend_abi.rs:6-33): C++ source of a cdylib.
+    std::string host_source() const;
+    std::vector<std::string> injection_lines;   // the `out[dest] += rate[k]` lines fused into the device dynamics (absent from the host twin)
 };
 
 CompiledModel compile_model(const ModelAst& ast);

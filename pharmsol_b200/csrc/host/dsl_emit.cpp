@@ -908,8 +908,12 @@ CompiledModel compile_model(const ModelAst& ast_in) {
         emit_fn(ast.kind == ModelKind::Sde ? "drift" : "dynamics", Role::Dynamics, ast.dynamics, sc_dyn, false);
         for (const auto& r : ast.routes) {
             const bool carries_infusion = !r.has_kind || r.kind == RouteKind::Infusion;
-            if (carries_infusion && !sc_dyn.routes_read.count(r.index))
-                S << "        out[" << r.dest_offset << "] += rate[" << r.index << "];   // infusion(" << r.name << ") -> state " << r.dest_offset << "\n";
+            if (carries_infusion && !sc_dyn.routes_read.count(r.index)) {
+                std::ostringstream inj;
+                inj << "        out[" << r.dest_offset << "] += rate[" << r.index << "];   // infusion(" << r.name << ") -> state " << r.dest_offset << "\n";
+                S << inj.str();
+                cm.injection_lines.push_back(inj.str());
+            }
         }
         for (auto& ri : cm.routes) ri.inject_input_to_destination = !sc_dyn.routes_read.count(ri.index);    // model_info.rs:151-154
         S << "    }\n";
@@ -1043,6 +1047,73 @@ std::string CompiledModel::cuda_source(const std::vector<std::pair<int, std::str
         for (const auto& e : entries) o << "    psi_aot_register(\"" << id << "\", " << e.first << ", (const void*)&" << e.second << ", \"" << e.second << "\");\n";
         o << "} } reg_" << id << "; }\n";
     }
+    return o.str();
+}
+
+// The host twin of the emitted model: the same function bodies as the CUDA translation unit, compiled by the system C++
+// compiler into a cdylib that exports the reference's frozen compiled-backend ABI (src/dsl/compiled_backend_abi.rs:6-33;
+// loader src/dsl/aot.rs:316-353, 404-470): pharmsol_dsl_api_version() == 2, the CompiledModelInfoEnvelope JSON, and one
+// `extern "C" fn(t, states, params, covariates, routes, derived, out)` per function role the model has.
+//  * dynamics / drift do NOT add the route inputs: the reference runtime injects them itself for routes with
+//    inject_input_to_destination (native.rs apply_route_inputs_to_rates), while the device dynamics has them fused in;
+//  * `out` may alias `states` (init) or `derived` (derive), as compiled_backend_abi.rs:147-180 allows;
+//  * route_lag / route_bioavailability write only the slots of routes that declare the property (the caller pre-fills
+//    0.0 / 1.0, native.rs:941-1018);
+//  * the pair-invariant slots the device code hoists into p[NP..] are recomputed per call from `params`.
+std::string CompiledModel::host_source() const {
+    std::string body = struct_body;
+    for (const auto& inj : injection_lines) {
+        const size_t at = body.find(inj);
+        if (at != std::string::npos) body.erase(at, inj.size());
+    }
+    auto b = [](bool v) { return v ? "true" : "false"; };
+    const bool ode = kind == ModelKind::Ode, sde = kind == ModelKind::Sde;
+    std::ostringstream env;
+    env << "{\"abi_version\": 2, \"model\": " << model_info_json() << ", \"functions\": {\"derive\": " << b(has_derive) << ", \"dynamics\": " << b(ode)
+        << ", \"outputs\": true, \"init\": " << b(has_init) << ", \"drift\": " << b(sde) << ", \"diffusion\": " << b(sde) << ", \"route_lag\": " << b(has_lag)
+        << ", \"route_bioavailability\": " << b(has_fa) << "}}";
+    std::ostringstream o;
+    o << "// generated by pharmsol-b200 dsl_emit from model `" << name << "` (id " << id << ") — host twin, frozen compiled-backend ABI; do not edit\n";
+    o << "#include <cmath>\n#include <cstddef>\n#include <cstdint>\n#include <cstdlib>\n#include <limits>\n";
+    o << "#define PSI_DEV inline\n";
+    o << "namespace psi {\n"
+         "inline double psi_nan() { return std::numeric_limits<double>::quiet_NaN(); }\n"
+         "inline double psi_inf() { return std::numeric_limits<double>::infinity(); }\n"
+         "inline double pow_half(double x) { return std::sqrt(x); }\n"
+         "inline double pow_quarter(double x) { return std::sqrt(std::sqrt(x)); }\n"
+         "inline double pow_three_quarters(double x) { const double s = std::sqrt(x); return s * std::sqrt(s); }\n"
+         "inline double pow_three_halves(double x) { return x * std::sqrt(x); }\n"
+         "inline double pow_2(double x) { return x * x; }\n"
+         "inline double pow_3(double x) { return (x * x) * x; }\n"
+         "inline double pow_4(double x) { const double q = x * x; return q * q; }\n"
+         "}  // namespace psi\n";
+    o << "namespace {\nstruct Model {\n" << body << "};\n";
+    o << "inline void load_params(const double* params, double* p) {\n    for (int k = 0; k < Model::NP; ++k) p[k] = params[k];\n    Model::prologue(p);\n}\n";
+    o << "const char kModelInfoJson[] = R\"PKMJSON(" << env.str() << ")PKMJSON\";\n}  // namespace\n";
+    o << "extern \"C\" {\n";
+    o << "uint32_t pharmsol_dsl_api_version(void) { return 2u; }\n";
+    o << "const uint8_t* pharmsol_dsl_model_info_json_ptr(void) { return reinterpret_cast<const uint8_t*>(kModelInfoJson); }\n";
+    o << "size_t pharmsol_dsl_model_info_json_len(void) { return sizeof(kModelInfoJson) - 1; }\n";
+    const char* sig = "(double t, const double* states, const double* params, const double* covariates, const double* routes, const double* derived, double* out)";
+    const char* pre = "    double p[Model::NPX > 0 ? Model::NPX : 1];\n    load_params(params, p);\n";
+    if (has_derive) o << "void pharmsol_dsl_kernel_derive" << sig << " {\n" << pre << "    (void)derived;\n    Model::derive(t, states, p, covariates, routes, out);\n}\n";
+    if (ode) o << "void pharmsol_dsl_kernel_dynamics" << sig << " {\n" << pre << "    Model::dynamics(t, states, p, covariates, routes, derived, out);\n}\n";
+    o << "void pharmsol_dsl_kernel_outputs" << sig << " {\n" << pre << "    Model::outputs(t, states, p, covariates, routes, derived, out);\n}\n";
+    if (has_init) o << "void pharmsol_dsl_kernel_init" << sig << " {\n" << pre << "    Model::init(t, states, p, covariates, routes, derived, out);\n}\n";
+    if (sde) {
+        o << "void pharmsol_dsl_kernel_drift" << sig << " {\n" << pre << "    Model::drift(t, states, p, covariates, routes, derived, out);\n}\n";
+        o << "void pharmsol_dsl_kernel_diffusion" << sig << " {\n" << pre << "    Model::diffusion(t, states, p, covariates, routes, derived, out);\n}\n";
+    }
+    auto route_fn = [&](const char* symbol, const char* member, bool lag) {
+        o << "void " << symbol << sig << " {\n" << pre;
+        for (const auto& r : routes)
+            if (lag ? r.has_lag : r.has_bioavailability)
+                o << "    out[" << r.index << "] = Model::" << member << "(" << r.index << ", t, states, p, covariates, routes, derived);\n";
+        o << "}\n";
+    };
+    if (has_lag) route_fn("pharmsol_dsl_kernel_route_lag", "lag", true);
+    if (has_fa) route_fn("pharmsol_dsl_kernel_route_bioavailability", "fa", false);
+    o << "}  // extern \"C\"\n";
     return o.str();
 }
 

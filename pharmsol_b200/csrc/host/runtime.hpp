@@ -72,6 +72,7 @@ struct Model {
     dsl::CompiledModel cm;
     psi::RunOpts opts;
     std::string source_cache;                 // generated CUDA C (for inspection)
+    std::string host_source_cache;            // generated host twin (frozen compiled-backend ABI), built on demand
     std::string info_json;
     std::map<int, KernelRef> kernels;         // by solver id
     std::string dsl_source;                   // as given to pharmsol_cuda_model_from_dsl (travels in the artifact)

@@ -48,3 +48,17 @@ def test_c_caller_matches_the_python_binding(ps, exe):
         assert row["psi_00"] == psi[0, 0]
         assert row["psi_sum"] == pytest.approx(float(np.sum(psi.ravel(order="F"))), rel=1e-13)
         assert 5.0 < row["us_per_matrix"] < 5000.0
+
+
+@pytest.mark.gpu
+def test_c_caller_multi_device_context(exe):
+    """SURVEY §8b `ctx_create(device_ids, n_dev)` from plain C: two column shards on GPU 0 (every visible GPU when there
+    are several) give the single-device matrix bit for bit, and the replicated call returns one matrix per device."""
+    import torch
+    n = torch.cuda.device_count()
+    devs = ",".join(str(k) for k in range(n)) if n > 1 else "0,0"
+    r = subprocess.run([exe, "--devices", devs, "4096"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    row = json.loads(r.stdout.strip().splitlines()[-1])
+    assert row["matches_single_device"] is True and row["replicated_ptrs"] is True and row["first_error_code"] == 0
+    assert row["devices"] == max(n, 2)
