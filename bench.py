@@ -531,6 +531,13 @@ def library_multi_device(env, rec, steps):
     w, eq, data, ems, psi, job = rec["_objects"]
     world = env.world
     out = None
+    # The other ranks must leave their GPUs idle while rank 0 drives all of them from one process: an NCCL barrier would
+    # keep a spinning kernel resident on every GPU (and time-slice against rank 0's launches there), so they block on the
+    # CPU-side rendezvous store instead.
+    store = env.dist.distributed_c10d._get_default_store()
+    env.barrier()
+    if env.rank != 0:
+        store.wait(["pharmsol_b200_library_multi_device_done"])
     if env.rank == 0:
         try:
             eq2, data2, ems2 = H.product_objects(w, device=list(range(world)))
@@ -563,6 +570,7 @@ def library_multi_device(env, rec, steps):
             _lib.host_free(p1); _lib.host_free(p2)
         except Exception as e:      # noqa: BLE001 - a failure here must not take the bench line down
             out = {"devices": world, "error": repr(e)}
+        store.set("pharmsol_b200_library_multi_device_done", "1")
     env.barrier()
     return out
 

@@ -185,6 +185,11 @@ int32_t pharmsol_cuda_model_set_max_steps(pcu_model* m, int32_t max_steps);
 /* with_particles (dsl/native.rs:2162) + stream seed + likelihood / stepper modes */
 int32_t pharmsol_cuda_model_set_particles(pcu_model* m, uint32_t nparticles, uint64_t seed, int32_t sde_mode,
                                           int32_t em_mode, double em_dt);
+/* Precision of the SDE noise draws: PCU_SDE_NORMALS_FP32 (default) = Box-Muller in FP32 on 24-bit Philox uniforms
+ * (|z| <= 5.77, SFU pipe); PCU_SDE_NORMALS_FP64 = the same transform in FP64 on 32-bit uniforms (|z| <= 6.66), ~the
+ * f64 `Normal` of the reference (sde/em.rs:104-120).  State, drift, diffusion and likelihood arithmetic is FP64 either way. */
+enum { PCU_SDE_NORMALS_FP32 = 0, PCU_SDE_NORMALS_FP64 = 1 };
+int32_t pharmsol_cuda_model_set_sde_normals(pcu_model* m, int32_t precision);
 int32_t pharmsol_cuda_model_set_cov_time(pcu_model* m, int32_t cov_time);
 /* build (or fetch) the device module now; returns the NVRTC log in last_error_message on failure.
  * *source_out (optional): 0 = ahead-of-time (nvcc, linked in), 1 = cubin cache, 2 = NVRTC, 3 = .pkm artifact */

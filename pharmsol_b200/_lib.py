@@ -114,6 +114,7 @@ def lib():
         "pharmsol_cuda_model_set_max_steps": (i32, [vp, i32]),
         "pharmsol_cuda_model_set_particles": (i32, [vp, C.c_uint32, C.c_uint64, i32, i32, d]),
         "pharmsol_cuda_model_set_cov_time": (i32, [vp, i32]),
+        "pharmsol_cuda_model_set_sde_normals": (i32, [vp, i32]),
         "pharmsol_cuda_model_compile": (i32, [vp, vp, P(i32)]),
         "pharmsol_cuda_model_precompile_to_cache": (i32, [vp, i32]),
         "pharmsol_cuda_population_create": (i32, [vp, vp, vp, P(pcu_error_model), i32, P(vp)]),
@@ -379,6 +380,9 @@ class Model:
 
     def set_particles(self, n, seed=0, sde_mode=0, em_mode=0, em_dt=0.0):
         check(lib().pharmsol_cuda_model_set_particles(self.ptr, int(n), int(seed), int(sde_mode), int(em_mode), float(em_dt)))
+
+    def set_sde_normals(self, precision):
+        check(lib().pharmsol_cuda_model_set_sde_normals(self.ptr, int(precision)))
 
     def set_cov_time(self, mode):
         check(lib().pharmsol_cuda_model_set_cov_time(self.ptr, int(mode)))

@@ -477,6 +477,7 @@ class SDE(Equation):
         self._np, self._seed, self._mode = int(st["nparticles"]), int(st["seed"]), int(st["sde_mode"])
         self._em, self._dt = int(st["em_mode"]), float(st["em_dt"])
         self._apply()
+        self._model.set_sde_normals(int(st.get("sde_normals", 0)))
 
     def with_particles(self, n):
         self._np = int(n)
@@ -496,6 +497,12 @@ class SDE(Equation):
     def with_stepper(self, em_mode, dt=0.05):
         self._em, self._dt = int(em_mode), float(dt)
         self._apply()
+        return self
+
+    def with_noise_precision(self, fp64=True):
+        """Noise draws in FP64 (Box-Muller on 32-bit uniforms) instead of the default FP32 / 24-bit ones; everything else
+        is FP64 either way (include/pharmsol_cuda.h PCU_SDE_NORMALS_*)."""
+        self._model.set_sde_normals(1 if fp64 else 0)
         return self
 
     def estimate_log_likelihood(self, subject, parameters, error_models):

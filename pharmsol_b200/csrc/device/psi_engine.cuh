@@ -107,6 +107,64 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
             }
         }
 
+        // ---- closed-form models without lag: execute the occasion's timeline program --------------------
+        // (psi_types.h EV_STEP: the host has already walked events / boundaries / infusions once per occasion;
+        //  the arithmetic per record is exactly what the generic walk below performs, so results are identical)
+        if constexpr (M::KIND == 1 && !M::HAS_LAG) {
+            const int pg0 = __ldg(pop.prog_offsets + occ), pg1 = __ldg(pop.prog_offsets + occ + 1);
+            for (int q = pg0; q < pg1; ++q) {
+                const EventRec e = load_event(pop.prog + q);
+                const int kind = ev_kind(e.meta);
+                if (kind == EV_STEP) {
+                    const double dt = e.a;
+                    if constexpr (NR == 1) { c.rate[0] = e.b; }
+                    else if constexpr (NR == 2) { c.rate[0] = e.b; c.rate[1] = e.w; }
+                    else if constexpr (NR == 3) { c.rate[0] = e.b; c.rate[1] = e.w; c.rate[2] = e.sigma; }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < NR; ++k) c.rate[k] = __ldg(pop.prog_rates + (long long)e.obs_row * NR + k);
+                    }
+                    if constexpr (!AK_HOISTED) {
+                        c.refresh(opt.cov_time == COVTIME_INTERVAL_LENGTH ? dt : e.time, x);
+                        double kp[8];
+                        M::kparams(c.p, c.d, kp);
+                        ak.setup_kp(kp, status);
+                    }
+                    ak.step(x, dt, c.rate[0]);
+                    cnt.evals++;
+                } else if (kind == EV_BOLUS) {
+                    const int route = ev_index(e.meta);
+                    double amount = e.a;
+                    if constexpr (M::HAS_FA) {
+                        double zx[AtLeast1<NS>::v];
+#pragma unroll
+                        for (int k = 0; k < AtLeast1<NS>::v; ++k) zx[k] = 0.0;
+                        c.zero_rate();
+                        c.refresh(e.time, zx);
+                        const double fa = M::fa(route, e.time, zx, c.p, c.cov, c.rate, c.d);
+                        if (fa != 1.0) amount *= fa;
+                    }
+                    const int dest = M::bolus_dest(route);
+                    if (dest < 0) { if (status == ST_OK) status = ST_UNSUPPORTED_INPUT_ROUTE_KIND; }
+                    add_at<AtLeast1<NS>::v>(x, dest, amount);
+                } else {
+                    if constexpr (M::OBS_USES_RATE) active_rates<NR>(inf, e.time, c.rate);
+                    c.refresh(e.time, x);
+                    double y[AtLeast1<M::NOUT>::v];
+#pragma unroll
+                    for (int k = 0; k < AtLeast1<M::NOUT>::v; ++k) y[k] = 0.0;
+                    M::outputs(e.time, x, c.p, c.cov, c.rate, c.d, y);
+                    const double yp = pick<AtLeast1<M::NOUT>::v>(y, ev_index(e.meta));
+                    if (pred && e.obs_row >= 0) pred[(long long)e.obs_row * pred_ld] = yp;
+                    if (opt.want_ll && ev_has_value(e.meta)) {
+                        if (opt.diagonal) ll += resid_log_likelihood(opt, ev_index(e.meta), e.a, yp);
+                        else ll += obs_log_likelihood(e, yp, status);
+                    }
+                }
+            }
+            continue;
+        }
+
         // ---- event cursor with per-thread lag ---------------------------------------------------
         auto lag_of = [&](int route, double tb) -> double {
             if constexpr (M::HAS_LAG) {
@@ -256,8 +314,31 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
                                                 long long spp_ld, const RunOpts& opt, const OutView& out) {
     const int nsub = (opt.nsub_limit > 0 && opt.nsub_limit < pop.nsub) ? opt.nsub_limit : pop.nsub;
     Counters cnt;
-    // one (subject, column slot) pair
-    auto do_pair = [&](int subj, long long q) {
+    // ONE inlined copy of the pair code serves the three index spaces (a copy per mode tripled the code and the register
+    // allocation is the maximum over all of them):
+    //   matrix       blockIdx.x * blockDim.x + threadIdx.x = column slot, blockIdx.y strides over subjects
+    //   warp tasks   few support points (a 128-column CTA per subject would idle most lanes): the warps of a 1-D grid
+    //                take (subject, 32-column chunk) tasks in order, so a CTA mixes subjects
+    //   diagonal     log_likelihood_batch: thread q = subject q with parameter row q
+    const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool wt = opt.warp_tasks != 0, diag = opt.diagonal != 0;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long nchunk = (ncols + 31) >> 5;
+    long long it, it_end, it_step;
+    if (wt) { it = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); it_end = nchunk * (long long)nsub; it_step = (long long)gridDim.x * wpb; }
+    else if (diag) { it = 0; it_end = (q0 < ncols) ? 1 : 0; it_step = 1; }
+    else { it = blockIdx.y; it_end = (q0 < ncols) ? nsub : 0; it_step = gridDim.y; }
+    for (; it < it_end; it += it_step) {
+        int subj;
+        long long q;
+        if (wt) {
+            subj = (int)(it / nchunk);
+            q = (it - (long long)subj * nchunk) * 32 + lane;
+            if (q >= ncols) continue;
+        } else {
+            subj = diag ? (int)q0 : (int)it;
+            q = q0;
+        }
         // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
         // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
         const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
@@ -266,10 +347,15 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
         M::prologue(c.p);
         int status = ST_OK;
-        double* pred = (opt.want_pred && out.pred) ? out.pred + j : nullptr;
+        double* pred = (opt.want_pred && out.pred && !diag) ? out.pred + j : nullptr;
         const unsigned int work0 = cnt.steps + cnt.rejected;
         double ll = run_pair<M, SOLVER>(pop, opt, subj, c, status, cnt, pred, out.ld_pred);
         if (out.col_work) atomicAdd(out.col_work + j, cnt.steps + cnt.rejected - work0);
+        if (diag) {
+            // a failed simulation scores -inf (likelihood/mod.rs:134-137)
+            if (out.ll) out.ll[q] = (status != ST_OK) ? -psi_inf() : ll;
+            continue;
+        }
         if (status != ST_OK) {
             ll = psi_nan();
             report_error(out, (long long)subj + (j + out.col_base) * (long long)pop.nsub, status);
@@ -282,35 +368,7 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         } else if (out.ll) {
             out.ll[(long long)subj + j * out.ld_ll] = ll;
         }
-    };
-    if (opt.warp_tasks) {
-        // Few support points: a 128-column CTA per subject would idle most lanes, so the warps of a 1-D grid take
-        // (subject, 32-column chunk) tasks in order and a CTA mixes subjects.
-        const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-        const long long nchunk = (ncols + 31) >> 5, ntask = nchunk * (long long)nsub;
-        for (long long task = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += (long long)gridDim.x * wpb) {
-            const long long q = (task % nchunk) * 32 + lane;
-            if (q < ncols) do_pair((int)(task / nchunk), q);
-        }
-        flush_counters(out, cnt);
-        return;
     }
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ncols) return;
-    if (opt.diagonal) {
-        // log_likelihood_batch: subject q with parameter row q; a failed simulation scores -inf (mod.rs:134-137)
-        PairCtx<M> c;
-#pragma unroll
-        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + q);
-        M::prologue(c.p);
-        int status = ST_OK;
-        double ll = run_pair<M, SOLVER>(pop, opt, (int)q, c, status, cnt, nullptr, 0);
-        if (status != ST_OK) ll = -psi_inf();
-        if (out.ll) out.ll[q] = ll;
-        flush_counters(out, cnt);
-        return;
-    }
-    for (int subj = blockIdx.y; subj < nsub; subj += gridDim.y) do_pair(subj, q);
     flush_counters(out, cnt);
 }
 

@@ -40,19 +40,37 @@ struct Philox {
     }
 };
 
-// Per-particle normal stream: Box-Muller on 24-bit uniforms in FP32 (SFU); one Philox block = 4 normals.
-// Everything is indexed statically so the normals stay in registers (a runtime-indexed buffer would
-// live in local memory).
+// Per-particle normal stream: one Philox block = 4 normals.  Everything is indexed statically so the normals stay in
+// registers (a runtime-indexed buffer would live in local memory).
+// Precision of the noise (RunOpts::sde_normals): the default draws Box-Muller normals in FP32 from 24-bit uniforms on the
+// SFU (MUFU.LG2 / SIN / COS): |z| <= 5.77, resolution 2^-24 near 0 — narrower than the f64 `Normal` the reference samples
+// (sde/em.rs:104-120), chosen because the stepper is bound by integer / SFU issue and an FP64 Box-Muller triples the cost
+// of a draw.  SDE_NORMALS_FP64 evaluates the same transform in FP64 from 32-bit uniforms (|z| <= 6.66); the particle-filter
+// likelihood does not distinguish the two (tests/test_gpu_sde_parity.py compares them at equal seed counts).
 struct NormalStream {
     Philox ph;
     unsigned int c0, c2, c3;   // particle slot, interval sequence, pair
     unsigned int ctr;          // draw-block counter within the interval
+    int fp64;                  // RunOpts::sde_normals
     PSI_DEV void reset(unsigned int particle, unsigned int seq, unsigned int pair) {
         c0 = particle; c2 = seq; c3 = pair; ctr = 0;
     }
-    PSI_DEV void block4(float* z) {
+    PSI_DEV void block4(double* z) {
         unsigned int r[4];
         ph(c0, ctr++, c2, c3, r);
+        if (fp64) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double u1 = ((double)r[2 * i] + 0.5) * (1.0 / 4294967296.0);      // (0,1), 32 bits
+                const double u2 = ((double)r[2 * i + 1] + 0.5) * (1.0 / 4294967296.0);
+                const double rad = sqrt(-2.0 * log(u1));
+                double sn, cs;
+                sincos(6.283185307179586 * u2, &sn, &cs);
+                z[2 * i] = rad * cs;
+                z[2 * i + 1] = rad * sn;
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float u1 = ((float)(r[2 * i] >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
@@ -60,13 +78,13 @@ struct NormalStream {
             const float rad = sqrtf(-2.0f * __logf(u1));
             float sn, cs;
             __sincosf(6.2831853071795865f * u2, &sn, &cs);
-            z[2 * i] = rad * cs;
-            z[2 * i + 1] = rad * sn;
+            z[2 * i] = (double)(rad * cs);
+            z[2 * i + 1] = (double)(rad * sn);
         }
     }
-    // COUNT normals into z[0..COUNT) (z must hold 4*ceil(COUNT/4) floats)
+    // COUNT normals into z[0..COUNT) (z must hold 4*ceil(COUNT/4) values)
     template <int COUNT>
-    PSI_DEV void fill(float* z) {
+    PSI_DEV void fill(double* z) {
 #pragma unroll
         for (int b = 0; b < (COUNT + 3) / 4; ++b) block4(z + 4 * b);
     }
@@ -146,22 +164,22 @@ struct SdeStep {
         M::diffusion(t, x, c.p, c.cov, c.rate, c.d, g);
     }
     // em.rs:104-120
-    PSI_DEV void em_step(double t, double dt, double sqdt, double* x, const float* z) {
+    PSI_DEV void em_step(double t, double dt, double sqdt, double* x, const double* z) {
         double dx[NS], g[NS];
         eval(t, x, dx, g);
 #pragma unroll
-        for (int k = 0; k < NS; ++k) x[k] = fma(dx[k], dt, fma(g[k] * (double)z[k], sqdt, x[k]));
+        for (int k = 0; k < NS; ++k) x[k] = fma(dx[k], dt, fma(g[k] * z[k], sqdt, x[k]));
     }
     // The full step y1 and the first half step of y2 both start from (t, x): one drift / diffusion evaluation serves
     // both (the reference evaluates it twice with identical arguments, em.rs:134-150).
-    PSI_DEV void em_first(double t, double dt, double sq, double sqh, const double* x, double* y1, double* y2, const float* z) {
+    PSI_DEV void em_first(double t, double dt, double sq, double sqh, const double* x, double* y1, double* y2, const double* z) {
         double dx[NS], g[NS];
         eval(t, x, dx, g);
         const double hdt = dt * 0.5;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            y1[k] = fma(dx[k], dt, fma(g[k] * (double)z[k], sq, x[k]));
-            y2[k] = fma(dx[k], hdt, fma(g[k] * (double)z[NS + k], sqh, x[k]));
+            y1[k] = fma(dx[k], dt, fma(g[k] * z[k], sq, x[k]));
+            y2[k] = fma(dx[k], hdt, fma(g[k] * z[NS + k], sqh, x[k]));
         }
     }
     // em.rs:134-167
@@ -171,7 +189,7 @@ struct SdeStep {
         while (t < tf) {
             if (++guard > 4000000) break;
             double y1[NS], y2[NS];
-            float z[4 * ((3 * NS + 3) / 4)];
+            double z[4 * ((3 * NS + 3) / 4)];
             rng.template fill<3 * NS>(z);                     // three INDEPENDENT draws per state (em.rs:104-120)
             const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
             em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
@@ -219,7 +237,7 @@ struct SdeStep {
                 t = t0; dt = 0.1; guard = 0; active = true;
             }
             double y1[NS], y2[NS];
-            float z[4 * ((3 * NS + 3) / 4)];
+            double z[4 * ((3 * NS + 3) / 4)];
             rng.template fill<3 * NS>(z);
             const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
             em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
@@ -256,7 +274,7 @@ struct SdeStep {
         // one Philox block yields 4 normals: take G = 4 / NS steps per block when NS < 4
         constexpr int G = (NS >= 4) ? 1 : 4 / NS;
         for (int i = 0; i < n; i += G) {
-            float z[4 * ((G * NS + 3) / 4)];
+            double z[4 * ((G * NS + 3) / 4)];
             rng.template fill<G * NS>(z);
 #pragma unroll
             for (int q = 0; q < G; ++q)
@@ -283,10 +301,13 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
         double* qv = ws + 2ll * NS * np;
         int* anc = reinterpret_cast<int*>(ws + 2ll * NS * np + np);
         Counters cnt;
-        const long long npairs = (long long)pop.nsub * ncols;
+        // log_likelihood_batch (likelihood/mod.rs:119-177): CTA q evaluates subject q with parameter row q; the score is the
+        // residual-error likelihood of the particle-MEAN predictions (estimate_predictions of an SDE, sde/mod.rs:387-433)
+        const bool diag = opt.diagonal != 0;
+        const long long npairs = diag ? (ncols < pop.nsub ? ncols : (long long)pop.nsub) : (long long)pop.nsub * ncols;
         for (long long lpair = blockIdx.x; lpair < npairs; lpair += gridDim.x) {
-            const int subj = (int)(lpair % pop.nsub);
-            const long long j = lpair / pop.nsub;
+            const int subj = diag ? (int)lpair : (int)(lpair % pop.nsub);
+            const long long j = diag ? lpair : lpair / pop.nsub;
             // the random streams are keyed by the GLOBAL pair index, so psi does not depend on how the columns are
             // sharded over GPUs or chunked by the host call
             const long long pair = (long long)subj + (j + out.col_base) * (long long)pop.nsub;
@@ -296,7 +317,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
             for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
             M::prologue(c.p);
             Philox ph{(unsigned int)(opt.seed & 0xffffffffull) ^ (unsigned int)(pair >> 32), (unsigned int)(opt.seed >> 32)};
-            NormalStream rng; rng.ph = ph;
+            NormalStream rng; rng.ph = ph; rng.fp64 = opt.sde_normals;
             int status = ST_OK;
             double ll = 0.0;
             unsigned int seq = 0;
@@ -365,7 +386,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                         if (dest < 0) { if (status == ST_OK) status = ST_UNSUPPORTED_INPUT_ROUTE_KIND; }
                         else for (int k = tid; k < np; k += B) cur_buf[(long long)dest * np + k] += amount;
                     } else if (kind == EV_OBS) {
-                        const bool pf = opt.want_ll && (opt.sde_mode == SDE_PARTICLE_FILTER) && ev_has_value(e.meta);
+                        const bool pf = opt.want_ll && !diag && (opt.sde_mode == SDE_PARTICLE_FILTER) && ev_has_value(e.meta);
                         double ysum = 0.0, qsum = 0.0;
                         int lstat = ST_OK;
                         for (int k = tid; k < np; k += B) {
@@ -436,6 +457,8 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                             }
                             __syncthreads();
                             double* t2 = cur_buf; cur_buf = alt_buf; alt_buf = t2;
+                        } else if (opt.want_ll && ev_has_value(e.meta) && diag) {
+                            ll += resid_log_likelihood(opt, ev_index(e.meta), e.a, ymean);
                         } else if (opt.want_ll && ev_has_value(e.meta) && opt.sde_mode == SDE_MEAN_PREDICTION) {
                             ll += obs_log_likelihood(e, ymean, status);
                         }
@@ -468,7 +491,9 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                     te = tn;
                 }
             }
-            if (tid == 0) {
+            if (tid == 0 && diag) {
+                if (out.ll) out.ll[lpair] = (status != ST_OK) ? -psi_inf() : ll;      // a failed simulation scores -inf (mod.rs:134-137)
+            } else if (tid == 0) {
                 if (status != ST_OK) { ll = psi_nan(); report_error(out, pair, status); }
                 if (out.npeers > 0) {
                     const long long at = (long long)subj + (j + out.col_base) * out.ld_ll;

@@ -22,7 +22,8 @@ typedef unsigned long long uint64_t;
 namespace psi {
 
 // ---- event kinds / flags (order = the reference's tie-break rank, data/event.rs:292-304) -------
-enum : int { EV_OBS = 0, EV_BOLUS = 1, EV_INFUSION = 2 };
+enum : int { EV_OBS = 0, EV_BOLUS = 1, EV_INFUSION = 2,
+             EV_STEP = 3 };   // timeline-program record only (PopView::prog): one propagation sub-interval, see below
 enum : int { CENS_NONE = 0, CENS_BLOQ = 1, CENS_ALOQ = 2 };
 
 // status codes == PharmsolError variants (src/error/mod.rs:14-49); shared with pharmsol_cuda.h
@@ -61,6 +62,15 @@ struct __attribute__((aligned(16))) EventRec {
     int32_t meta;     // bits 0-1 kind | 2-3 censoring | 4 has_value | 8-15 input/outeq index | 16-23 host status
     int32_t obs_row;  // row of this observation in the predictions output (global over the population), -1 otherwise
 };
+// Timeline program (closed-form models without lag: nothing about the event walk depends on the support point).  The host
+// flattener runs the reference's interval logic ONCE per occasion — consecutive events, interior infusion boundaries
+// with the 1e-12 de-duplication (analytical/mod.rs:311-327), the rates active on each sub-interval (:337-357) — and
+// emits a flat list of records the device executes in order:
+//   EV_BOLUS / EV_OBS   the event record unchanged (infusion events carry no action and are dropped)
+//   EV_STEP             time = sub-interval end, a = dt (the same IEEE difference the device formed per pair),
+//                       b / w / sigma = rate of route 0 / 1 / 2 on the sub-interval; with more than 3 routes obs_row
+//                       indexes PopView::prog_rates (route_len doubles per step)
+// so a pair costs one broadcast load + arithmetic per record: no cursor, no boundary scan, no infusion scan.
 __host__ __device__ inline int ev_kind(int meta) { return meta & 3; }
 __host__ __device__ inline int ev_cens(int meta) { return (meta >> 2) & 3; }
 __host__ __device__ inline int ev_has_value(int meta) { return (meta >> 4) & 1; }
@@ -99,6 +109,9 @@ struct PopView {
     const int32_t* cov_offsets;   // [nocc*ncov+1]  segments of covariate c in occasion o = [cov_offsets[o*ncov+c], ...+1)
     const CovSeg* cov_segs;
     const double* occ_t0;         // [nocc]     occasion.initial_time() (ODE t0, data/structs.rs:782-793)
+    const int32_t* prog_offsets;  // [nocc+1]   timeline program of the occasion (models without lag; nullptr otherwise)
+    const EventRec* prog;         // [nprog]
+    const double* prog_rates;     // [nstep * route_len]  only when route_len > 3
     int32_t nsub;
     int32_t ncov;
     int32_t max_events;           // max events in any occasion
@@ -112,6 +125,7 @@ enum : int { SOLVER_DOPRI5 = 0, SOLVER_TSIT5 = 1, SOLVER_SDIRK4 = 2, SOLVER_TRBD
 enum : int { COVTIME_INTERVAL_END = 0, COVTIME_INTERVAL_LENGTH = 1 };
 enum : int { SDE_MEAN_PREDICTION = 0, SDE_PARTICLE_FILTER = 1 };
 enum : int { EM_REFERENCE_ADAPTIVE = 0, EM_FIXED_STEP = 1 };
+enum : int { SDE_NORMALS_FP32 = 0, SDE_NORMALS_FP64 = 1 };
 
 // ResidualErrorModel (data/residual_error.rs:69-139): prediction-based sigma, evaluated on the device.
 enum : int { RESID_MISSING = 0, RESID_CONSTANT = 1, RESID_PROPORTIONAL = 2, RESID_COMBINED = 3, RESID_EXPONENTIAL = 4 };
@@ -142,7 +156,7 @@ struct RunOpts {
     int32_t diagonal;
     int32_t warp_tasks;       // few support points (< 128): warp w of the 1-D grid takes (subject, 32-column chunk) task w
     int32_t nresid;
-    int32_t pad3_;
+    int32_t sde_normals;      // SDE noise: 0 = FP32 Box-Muller on 24-bit uniforms (default), 1 = FP64 Box-Muller on 32-bit uniforms
     ResidErr resid[PSI_MAX_RESID];
 };
 

@@ -456,6 +456,11 @@ int32_t pharmsol_cuda_model_set_particles(pcu_model* m, uint32_t n, uint64_t see
     if (em_dt > 0) m->m.opts.em_dt = em_dt;
     return PCU_OK;
 }
+int32_t pharmsol_cuda_model_set_sde_normals(pcu_model* m, int32_t precision) {
+    if (!m || precision < 0 || precision > 1) return PCU_ERR_INVALID_ARGUMENT;
+    m->m.opts.sde_normals = precision;
+    return PCU_OK;
+}
 int32_t pharmsol_cuda_model_set_cov_time(pcu_model* m, int32_t mode) {
     if (!m || mode < 0 || mode > 1) return PCU_ERR_INVALID_ARGUMENT;
     m->m.opts.cov_time = mode;
@@ -951,7 +956,6 @@ int32_t pharmsol_cuda_log_likelihood_batch(pcu_ctx* ctx, pcu_model* m, pcu_popul
         if (np != (int32_t)m->m.cm.parameters.size())
             throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
                                                    " parameter value(s), got " + std::to_string(np));
-        if (m->m.cm.kind == dsl::ModelKind::Sde) throw PharmsolError(PCU_ERR_OTHER, "log_likelihood_batch is not available for SDE models on the device");
         if (n_models > psi::PSI_MAX_RESID) throw PharmsolError(PCU_ERR_OTHER, "at most " + std::to_string(psi::PSI_MAX_RESID) + " residual error models");
         if (nsub == 0) return (int32_t)PCU_OK;
         std::lock_guard<std::mutex> lk(ctx->c.mu);

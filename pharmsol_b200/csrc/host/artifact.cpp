@@ -36,7 +36,7 @@ std::string settings_text(const psi::RunOpts& o) {
     std::ostringstream os;
     os.precision(17);
     os << "solver=" << o.solver << "\nrtol=" << o.rtol << "\natol=" << o.atol << "\nmax_steps=" << o.max_steps << "\nnparticles=" << o.nparticles
-       << "\nseed=" << o.seed << "\nsde_mode=" << o.sde_mode << "\nem_mode=" << o.em_mode << "\nem_dt=" << o.em_dt << "\ncov_time=" << o.cov_time << "\n";
+       << "\nseed=" << o.seed << "\nsde_mode=" << o.sde_mode << "\nem_mode=" << o.em_mode << "\nem_dt=" << o.em_dt << "\ncov_time=" << o.cov_time << "\nsde_normals=" << o.sde_normals << "\n";
     return os.str();
 }
 }  // namespace
@@ -71,12 +71,13 @@ void apply_artifact_settings(const std::string& text, psi::RunOpts& o) {
         else if (k == "em_mode") o.em_mode = std::stoi(v);
         else if (k == "em_dt") o.em_dt = std::stod(v);
         else if (k == "cov_time") o.cov_time = std::stoi(v);
+        else if (k == "sde_normals") o.sde_normals = std::stoi(v);
     }
     // the same ranges the pharmsol_cuda_model_set_* entry points enforce: the checksum only detects corruption, a
     // well-formed file can still carry values no setter would accept
     const bool ok = o.solver >= 0 && o.solver < psi::SOLVER_COUNT && o.rtol > 0.0 && o.atol > 0.0 && std::isfinite(o.rtol) && std::isfinite(o.atol) &&
                     o.max_steps > 0 && o.nparticles > 0 && o.sde_mode >= 0 && o.sde_mode <= 1 && o.em_mode >= 0 && o.em_mode <= 1 &&
-                    o.em_dt > 0.0 && std::isfinite(o.em_dt) && o.cov_time >= 0 && o.cov_time <= 1;
+                    o.em_dt > 0.0 && std::isfinite(o.em_dt) && o.cov_time >= 0 && o.cov_time <= 1 && o.sde_normals >= 0 && o.sde_normals <= 1;
     if (!ok) throw PharmsolError(psi::ST_OTHER, "artifact has invalid settings");
 }
 

@@ -168,8 +168,13 @@ FlatPopulation flatten_population(const Data& data, const ModelLabels& labels, c
     f.obs_offsets.push_back(0);
     const double inf = std::numeric_limits<double>::infinity();
     int32_t obs_row = 0;
+    f.has_prog = true;
+    for (const auto& r : labels.routes) if (r.has_lag) f.has_prog = false;      // lagged bolus times depend on the support point
+    const int nroute = std::max(1, labels.route_len);
+    f.prog_offsets.push_back(0);
     for (const auto& subj : data.subjects) {
         for (const auto& occ : subj.occasions) {
+            const size_t ev_first = f.events.size(), inf_first = f.infs.size();
             f.occ_index.push_back(occ.index);
             f.occ_t0.push_back(occ.initial_time());
             std::vector<double> bounds;
@@ -221,6 +226,52 @@ FlatPopulation flatten_population(const Data& data, const ModelLabels& labels, c
             std::sort(bounds.begin(), bounds.end());
             bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
             f.bnds.insert(f.bnds.end(), bounds.begin(), bounds.end());
+            if (f.has_prog) {
+                // The walk psi_engine.cuh performs per pair (event -> next event, split at interior boundaries), once.
+                size_t abc = 0;
+                std::vector<double> rate((size_t)nroute);
+                for (size_t k = ev_first; k < f.events.size(); ++k) {
+                    const EventRec& e = f.events[k];
+                    if (ev_kind(e.meta) != EV_INFUSION) f.prog.push_back(e);
+                    if (k + 1 >= f.events.size()) break;
+                    const double te = e.time, tn = f.events[k + 1].time;
+                    if (te == tn) continue;
+                    double last = te;
+                    while (abc < bounds.size() && bounds[abc] <= te) ++abc;
+                    while (true) {
+                        while (abc < bounds.size()) {       // candidates the reference's 1e-12 dedup would remove
+                            const double bq = bounds[abc];
+                            if (bq <= last || std::fabs(bq - last) < 1e-12) ++abc; else break;
+                        }
+                        double nxt;
+                        const double bq = abc < bounds.size() ? bounds[abc] : inf;
+                        if (bq < tn) { nxt = bq; ++abc; }
+                        else if (tn > last && !(std::fabs(tn - last) < 1e-12)) nxt = tn;
+                        else break;
+                        std::fill(rate.begin(), rate.end(), 0.0);
+                        for (size_t q = inf_first; q < f.infs.size(); ++q) {      // interval_route_inputs, analytical/mod.rs:337-357
+                            const InfRec& ir = f.infs[q];
+                            if (last >= ir.time && nxt <= ir.time + ir.duration && ir.input >= 0 && ir.input < nroute) rate[(size_t)ir.input] += ir.rate;
+                        }
+                        EventRec s{};
+                        s.time = nxt;
+                        s.a = nxt - last;
+                        s.b = rate[0];
+                        s.w = nroute > 1 ? rate[1] : 0.0;
+                        s.sigma = nroute > 2 ? rate[2] : 0.0;
+                        s.meta = ev_pack(EV_STEP, 0, 0, 0, 0);
+                        s.obs_row = -1;
+                        if (nroute > 3) {
+                            s.obs_row = (int32_t)(f.prog_rates.size() / (size_t)nroute);
+                            f.prog_rates.insert(f.prog_rates.end(), rate.begin(), rate.end());
+                        }
+                        f.prog.push_back(s);
+                        last = nxt;
+                        if (nxt == tn) break;
+                    }
+                }
+            }
+            f.prog_offsets.push_back((int32_t)f.prog.size());
             // covariate segments (covariate.rs:189-212) with a leading sentinel for t < first
             for (const auto& cname : labels.covariates) {
                 auto it = occ.covariates.find(cname);

@@ -133,6 +133,12 @@ struct FlatPopulation {
     std::vector<double> bnds, occ_t0;
     std::vector<psi::CovSeg> cov_segs;
     std::vector<int32_t> obs_offsets;   // [nsub+1] prefix sums of observation counts (prediction rows)
+    // timeline program (psi_types.h): built when no route of the model declares a lag, i.e. when event times do not
+    // depend on the support point; the closed-form kernels execute it instead of walking events / boundaries / infusions
+    std::vector<int32_t> prog_offsets;
+    std::vector<psi::EventRec> prog;
+    std::vector<double> prog_rates;
+    bool has_prog = false;
     int32_t nsub = 0, ncov = 0, max_events = 0;
     int64_t nobs_total = 0;
     bool has_lagged_candidates = false;

@@ -1016,6 +1016,8 @@ CompiledModel compile_model(const ModelAst& ast_in) {
       << ", HAS_LAG = " << (cm.has_lag ? "true" : "false") << ", HAS_FA = " << (cm.has_fa ? "true" : "false") << ";\n";
     H << "    static constexpr bool RHS_USES_COV = " << (rhs_uses_cov ? "true" : "false") << ", RHS_USES_DERIVED = " << (dyn_reads_derived ? "true" : "false")
       << ", KP_USES_DERIVED = " << (kp_uses_derived ? "true" : "false") << ", RHS_TIME_DEP = " << (rhs_time_dep ? "true" : "false") << ";\n";
+    // do the outputs (directly or through derive) read rate(route)?  If not, an observation needs no infusion scan
+    H << "    static constexpr bool OBS_USES_RATE = " << ((((sc_out.deps | sc_derive.deps) & DEP_RATE) != 0) ? "true" : "false") << ";\n";
     // pair-invariant slots: evaluated once per (subject, support point) pair right after the parameter load
     S << "    PSI_DEV static void prologue(double* p) {\n";
     for (size_t k = 0; k < em.slots.size(); ++k) S << "        p[" << (cm.parameters.size() + k) << "] = " << em.slots[k] << ";\n";

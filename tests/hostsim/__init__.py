@@ -141,7 +141,8 @@ class HostSim:
         self.nsub = len(subjects)
         return self
 
-    def run(self, support_points, error_models=None, solver="Dopri5", rtol=1e-4, atol=1e-4, cov_time=0, max_steps=200000, want_pred=False):
+    def run(self, support_points, error_models=None, solver="Dopri5", rtol=1e-4, atol=1e-4, cov_time=0, max_steps=200000, want_pred=False,
+            particles=1, seed=0x5EED, sde_mode=0, em_mode=0, em_dt=0.05, sde_normals=0):
         """error_models: list per output of None | (kind:int 1 additive / 2 proportional, factor, (c0..c3)).
         Returns (psi F-order (nsub, nspp), predictions (nobs, nspp) | None, info)."""
         spp = np.ascontiguousarray(support_points, dtype=np.float64)
@@ -157,7 +158,8 @@ class HostSim:
         if want_pred:
             nobs = self.lib.hs_nobs(self.h, None, 0)
             pred = np.full((nobs, nspp), np.nan)
-        opts = np.array([rtol, atol, float(cov_time), float(max_steps), 0.0])
+        opts = np.array([rtol, atol, float(cov_time), float(max_steps), 0.0, float(particles), float(seed), float(sde_mode), float(em_mode), float(em_dt),
+                         float(sde_normals)])
         code, pair = C.c_int(0), C.c_long(-1)
         counters = (C.c_ulonglong * 4)()
         rc = self.lib.hs_run(self.h, SOLVERS[solver] if isinstance(solver, str) else int(solver), dp(spp), nspp, npar, dp(ems), nem, dp(opts),

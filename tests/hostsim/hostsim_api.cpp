@@ -86,7 +86,10 @@ long hs_nobs(void* p, const double* ems, int nem) {
     try { return (long)flatten_population(h->data, h->cm.labels(), nullptr).nobs_total; } catch (const std::exception& e) { h->error = e.what(); return -1; }
 }
 
-// ems: nem rows of {kind, factor, c0, c1, c2, c3}; opts: {rtol, atol, cov_time, max_steps, h0}
+// ems: nem rows of {kind, factor, c0, c1, c2, c3}; opts: {rtol, atol, cov_time, max_steps, h0, nparticles, seed, sde_mode, em_mode, em_dt, sde_normals}
+// SDE models run with ONE thread per CTA (blockDim.x = 1): every cooperative loop of the kernel degenerates to a serial
+// loop and the block reductions to one lane, so the same source runs unchanged (sums are formed in a different order
+// than with 128 threads: results agree with the device to rounding, not bit for bit).
 // out_ll: F-order (nsub x nspp); out_pred: (nobs x nspp) row-major or NULL; counters[4]
 int hs_run(void* p, int solver, const double* spp_rows, long nspp, int np, const double* ems, int nem, const double* o, double* out_ll, double* out_pred,
            int* code, long* pair, unsigned long long* counters) {
@@ -106,13 +109,16 @@ int hs_run(void* p, int solver, const double* spp_rows, long nspp, int np, const
         v.bol_offsets = f.bol_offsets.data(); v.bol_event = f.bol_event.data(); v.inf_offsets = f.inf_offsets.data(); v.infs = f.infs.data();
         v.bnd_offsets = f.bnd_offsets.data(); v.bnds = f.bnds.data(); v.cov_offsets = f.cov_offsets.data(); v.cov_segs = f.cov_segs.data();
         v.occ_t0 = f.occ_t0.data(); v.nsub = f.nsub; v.ncov = f.ncov; v.max_events = f.max_events;
+        v.prog_offsets = f.has_prog ? f.prog_offsets.data() : nullptr; v.prog = f.has_prog ? f.prog.data() : nullptr;
+        v.prog_rates = f.has_prog ? f.prog_rates.data() : nullptr;
         std::vector<double> soa((size_t)np * nspp);
         for (long j = 0; j < nspp; ++j)
             for (int k = 0; k < np; ++k) soa[(size_t)k * nspp + j] = spp_rows[(size_t)j * np + k];
         psi::RunOpts opt;
         std::memset(&opt, 0, sizeof opt);
         opt.rtol = o[0]; opt.atol = o[1]; opt.cov_time = (int)o[2]; opt.max_steps = (int)o[3]; opt.h0 = o[4];
-        opt.em_dt = 0.05; opt.solver = solver; opt.nparticles = 1; opt.want_ll = out_ll ? 1 : 0; opt.want_pred = out_pred ? 1 : 0;
+        opt.solver = solver; opt.want_ll = out_ll ? 1 : 0; opt.want_pred = out_pred ? 1 : 0;
+        opt.nparticles = (int)o[5]; opt.seed = (unsigned long long)o[6]; opt.sde_mode = (int)o[7]; opt.em_mode = (int)o[8]; opt.em_dt = o[9]; opt.sde_normals = (int)o[10];
         unsigned long long status[5] = {~0ull, 0, 0, 0, 0};
         psi::OutView out{};
         out.ll = out_ll; out.ld_ll = f.nsub; out.pred = out_pred; out.ld_pred = nspp; out.first_error = status; out.counters = status + 1;
@@ -120,6 +126,20 @@ int hs_run(void* p, int solver, const double* spp_rows, long nspp, int np, const
         const std::string name = "psi_entry_" + h->cm.id + "_s" + std::to_string(s_eff);
         entry_fn fn = (entry_fn)dlsym(RTLD_DEFAULT, name.c_str());
         if (!fn) { h->error = "entry " + name + " is not linked into this hostsim module"; return 15; }
+        if (h->cm.kind == dsl::ModelKind::Sde) {
+            const int np_ = opt.nparticles > 0 ? opt.nparticles : 1;
+            const long long stride = ((2LL * h->cm.state_len + 2) * np_ + 64) / 32 * 32;
+            std::vector<double> scratch((size_t)stride);
+            out.scratch = scratch.data();
+            out.scratch_stride = 0;              // one CTA at a time: every CTA reuses the same slab
+            blockDim.x = 1; gridDim.x = (unsigned)((long long)f.nsub * nspp); gridDim.y = 1;
+            threadIdx.x = 0; blockIdx.y = 0;
+            for (unsigned bx = 0; bx < gridDim.x; ++bx) { blockIdx.x = bx; fn(v, soa.data(), nspp, nspp, opt, out); }
+            for (int k = 0; k < 4; ++k) counters[k] = status[1 + k];
+            if (status[0] == ~0ull) { *code = 0; *pair = -1; }
+            else { *code = (int)(status[0] & 0xff); *pair = (long)(status[0] >> 8); }
+            return 0;
+        }
         const pharmsol::LaunchGeometry g = pharmsol::psi_launch_geometry(f.nsub, nspp, false, 148, 128);
         opt.warp_tasks = g.warp_tasks;
         blockDim.x = g.block; gridDim.x = g.grid_x; gridDim.y = g.grid_y;

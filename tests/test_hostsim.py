@@ -84,3 +84,81 @@ def test_esdirk34_observed_order_is_three(HS):
         _, pred, info = hs.run(np.array([[1.0]]), None, solver="Esdirk34", rtol=tol, atol=tol, want_pred=True)
         errs.append(abs(pred[0, 0] - exact))
     assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-7
+
+
+def _random_subject(rng, absorb, n_occ):
+    ops = []
+    grid = np.round(rng.uniform(0.0, 48.0, 40) * 4) / 4          # quarter-hour grid -> plenty of exact ties
+    for occ in range(n_occ):
+        if occ:
+            ops.append(("reset",))
+        for _ in range(rng.integers(1, 5)):
+            ops.append(("bolus", float(rng.choice(grid)), float(rng.uniform(10, 500)), "1" if (absorb and rng.random() < 0.4) else "0"))
+        for _ in range(rng.integers(0, 4)):
+            ops.append(("infusion", float(rng.choice(grid)), float(rng.uniform(10, 500)), "0", float(rng.choice([0.25, 0.5, 1.0, 3.0, 7.5]))))
+        for _ in range(rng.integers(1, 12)):
+            t = float(rng.choice(grid))
+            ops.append(("missing_observation", t, "0") if rng.random() < 0.3 else ("observation", t, float(rng.uniform(0.1, 20.0)), "0"))
+    return ops
+
+
+@pytest.mark.parametrize("kernel", ["one_compartment", "two_compartments_with_absorption", "three_compartments_cl", "three_compartments_with_absorption"])
+def test_timeline_program_on_random_timelines(HS, oracle, kernel):
+    """The host-built timeline program (psi_types.h EV_STEP) against the oracle's literal event walk: overlapping
+    infusions, exact ties between observations / boluses / infusion boundaries, several occasions, missing observations."""
+    rng = np.random.default_rng(sum(kernel.encode()) + 7)
+    absorb = kernel.endswith("with_absorption")
+    subjects = [(f"r{i}", _random_subject(rng, absorb, int(rng.integers(1, 4)))) for i in range(10)]
+    names = FX.KERNEL_PARAMS[kernel]
+    nspp = 24
+
+    def draw(name):
+        if name in ("v", "vc", "vp", "v2", "v3"):
+            return rng.uniform(5.0, 80.0, nspp)
+        if name in ("cl", "q", "q2", "q3"):
+            return rng.uniform(0.5, 20.0, nspp)
+        return rng.uniform(0.02, 2.5, nspp)
+    spp = np.stack([draw(n) for n in names], axis=1)
+    em = ("additive", 0.05, (0.1, 0.15, 0.0, 0.0))
+    hs = HS(FX.kernel_dsl(kernel)).set_subjects(subjects)
+    psi, pred, info = hs.run(spp, [(1, em[1], em[2])], want_pred=True)
+    om = oracle.Model(kernel)
+    od = oracle.Data([oracle.Subject(o, i) for i, o in subjects])
+    ref = om.log_likelihood_matrix(od, spp, oracle.ErrorModels([em]))
+    nobs = max(sum(1 for o in ops if o[0] == "observation") for _, ops in subjects)
+    bar = 1e-11 if kernel.startswith("three") else 1e-12
+    assert info["code"] == 0 and _scaled(psi, ref, nobs) <= bar
+    row = 0
+    for i, (_, ops) in enumerate(subjects):
+        n = sum(1 for o in ops if o[0] in ("observation", "missing_observation"))
+        for j in range(4):
+            want = om.predictions(od.subjects[i], spp[j])
+            got = pred[row:row + n, j]
+            floor = 1e-9 * max(1.0, np.max(np.abs(want)))
+            assert np.max(np.abs(got - want) / np.maximum(np.abs(want), floor)) <= 2 * bar, (kernel, i, j)
+        row += n
+
+
+def test_lagged_model_keeps_the_per_pair_event_walk(HS, oracle):
+    """A model WITH lag cannot use the timeline program (bolus times depend on the support point): the generic cursor
+    path must still agree with the oracle's lag / re-sort semantics (data/structs.rs:611-690)."""
+    src, twin, p, ops, _ = FX.CORPUS["analytical_full"]
+    hs = HS(src).set_subjects([("s", ops)])
+    _, pred, info = hs.run(np.array([p]), None, want_pred=True)
+    want = oracle.Model(twin).predictions(oracle.Subject(ops), p)
+    assert info["code"] == 0 and np.max(np.abs(pred[:, 0] - want) / np.maximum(np.abs(want), 1e-10)) <= 1e-12
+
+
+def test_sde_kernel_source_runs_single_threaded(HS, oracle):
+    """The cooperative SDE kernel with one thread per CTA: zero diffusion reproduces the deterministic solution, the
+    FP32- and FP64-noise paths agree far inside one seed-to-seed standard deviation (see tests/test_gpu_sde_parity.py)."""
+    from benches import workloads as W
+    w = W.make("c5", nsub=2, nspp=3, particles=96)
+    hs = HS(w["dsl"]).set_subjects(w["subjects"])
+    ems = _ems(w)
+    kw = dict(particles=96, sde_mode=1, em_mode=1, em_dt=0.02)
+    a = hs.run(w["support_points"], ems, seed=5, **kw)[0]
+    b = hs.run(w["support_points"], ems, seed=5, sde_normals=1, **kw)[0]
+    c = hs.run(w["support_points"], ems, seed=6, **kw)[0]
+    assert np.all(np.isfinite(a)) and not np.array_equal(a, b)
+    assert np.abs(a - b).max() <= 1e-3 * np.abs(a - c).max()
