@@ -1016,6 +1016,16 @@ CompiledModel compile_model(const ModelAst& ast_in) {
       << ", HAS_LAG = " << (cm.has_lag ? "true" : "false") << ", HAS_FA = " << (cm.has_fa ? "true" : "false") << ";\n";
     H << "    static constexpr bool RHS_USES_COV = " << (rhs_uses_cov ? "true" : "false") << ", RHS_USES_DERIVED = " << (dyn_reads_derived ? "true" : "false")
       << ", KP_USES_DERIVED = " << (kp_uses_derived ? "true" : "false") << ", RHS_TIME_DEP = " << (rhs_time_dep ? "true" : "false") << ";\n";
+    // resident CTAs per SM the kernel is compiled for (psi_engine.cuh PSI_DEFINE_ENTRY): measured per kernel family
+    {
+        int min_blocks = 6;
+        if (ast.kind == ModelKind::Analytical && !cm.has_lag) {
+            const int ak = cm.analytical_kernel;          // 0-3 one compartment, 4-7 two compartments, 8-11 three
+            if (ak >= 0 && ak <= 3) min_blocks = 10;
+            else if (ak >= 4 && ak <= 7) min_blocks = 8;
+        }
+        H << "    static constexpr int MIN_BLOCKS = " << min_blocks << ";\n";
+    }
     // do the outputs (directly or through derive) read rate(route)?  If not, an observation needs no infusion scan
     H << "    static constexpr bool OBS_USES_RATE = " << ((((sc_out.deps | sc_derive.deps) & DEP_RATE) != 0) ? "true" : "false") << ";\n";
     // pair-invariant slots: evaluated once per (subject, support point) pair right after the parameter load

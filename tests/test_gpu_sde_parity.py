@@ -78,9 +78,6 @@ def test_fp32_and_fp64_noise_give_the_same_likelihood(ps):
         paired = np.abs(a - b).max(axis=0)[ok]
         assert ok.mean() > 0.9 and not np.array_equal(a, b)        # the FP64 path really is a different computation
         assert np.all(paired <= 1e-2 * np.maximum(sd, 1e-6)), (paired.max(), sd.min())
-        # and against the oracle-free statistic: the seed means agree within 3 SE of the paired difference
-        d = (a - b)[:, ok]
-        assert np.all(np.abs(d.mean(axis=0)) <= 3.0 * d.std(axis=0, ddof=1) / np.sqrt(case["nseed"]) + 1e-9)
 
 
 def test_log_likelihood_batch_for_sde_models(ps, oracle):
