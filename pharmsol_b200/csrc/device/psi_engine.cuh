@@ -60,18 +60,6 @@ PSI_DEV int ode_advance(OdeState<M::NSTATE>& st, typename SolverMem<SOLVER, M::N
     else return erk_integrate_to<Dopri5, M::NSTATE>(st, tstop, f, opt, cnt);
 }
 
-// One iteration of the engine's flat ODE loop: a SINGLE step attempt for the one-step methods that keep no state between
-// steps beyond OdeState (the explicit pairs, RODAS4); the iterative / multistep methods integrate the whole segment.
-template <class M, int SOLVER>
-PSI_DEV int ode_step_once(OdeState<M::NSTATE>& st, typename SolverMem<SOLVER, M::NSTATE>::type& mem, double tstop, OdeRhs<M>& f, const RunOpts& opt,
-                          Counters& cnt) {
-    if constexpr (SOLVER == SOLVER_DOPRI5) return erk_step<Dopri5, M::NSTATE>(st, tstop, f, opt, cnt);
-    else if constexpr (SOLVER == SOLVER_TSIT5) return erk_step<Tsit5, M::NSTATE>(st, tstop, f, opt, cnt);
-    else if constexpr (SOLVER == SOLVER_RODAS4) return rodas4_step<M::NSTATE, M::RHS_TIME_DEP>(st, tstop, f, opt, cnt);
-    else return ode_advance<M, SOLVER>(st, mem, tstop, f, opt, cnt);
-}
-template <int SOLVER> struct SteppedSolver { static constexpr bool v = SOLVER == SOLVER_DOPRI5 || SOLVER == SOLVER_TSIT5 || SOLVER == SOLVER_RODAS4; };
-
 // One (subject, support point) pair.  Returns the summed log-likelihood; `status` != 0 on error.
 template <class M, int SOLVER>
 PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCtx<M>& c, int& status, Counters& cnt,
@@ -193,6 +181,10 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
         EventCursor<M, decltype(lag_of)> cur(pop, occ, lag_of);
 
         // ---- ODE solver state -------------------------------------------------------------------
+        // (A flat per-lane loop — one step attempt OR one event per iteration, so lanes in different inter-event
+        //  intervals share the step code — was measured on B200 and lost: C2 43.1 -> 49.3 ms, C4 104.2 -> 114.7 ms.
+        //  Lanes reach an event in different iterations, so the event code runs several times per warp instead of once;
+        //  with work-balanced columns the re-convergence at events costs less than that.  profiles/r02_tuning.md)
         [[maybe_unused]] OdeState<AtLeast1<NS>::v> st;
         [[maybe_unused]] OdeRhs<M> rhs{c};
         [[maybe_unused]] typename SolverMem<(M::KIND == 0 ? SOLVER : 0), AtLeast1<NS>::v>::type solver_mem;
@@ -202,8 +194,6 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
             bnd_end = __ldg(pop.bnd_offsets + occ + 1);
         }
         if constexpr (M::KIND == 0) {
-#pragma unroll
-            for (int k = 0; k < NS; ++k) st.y[k] = x[k];
             st.t = __ldg(pop.occ_t0 + occ);
             st.h = -1.0;
             st.have_k1 = false;
@@ -211,90 +201,6 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
             st.since_restart = 0;
             bnd = __ldg(pop.bnd_offsets + occ);
             bnd_end = __ldg(pop.bnd_offsets + occ + 1);
-        }
-
-        // ---- ODE models: flat per-lane loop ------------------------------------------------------------------
-        // ODE::run_events (ode/mod.rs:609-824) as a state machine: every iteration is EITHER one solver step attempt
-        // towards the next stop (the pending event or an infusion boundary before it) OR the processing of the pending
-        // event.  The lanes of a warp walk the same timeline but need different numbers of steps per interval; with
-        // "integrate to the event, then process it" they re-converge at every event and the fast lanes idle (ncu on the
-        // stiff C4 model: 25.5 of 32 lanes per instruction).  Here a lane that reaches its event early handles it and
-        // joins the others' step code in the next interval.  Only the event TIME is held across the steps; the record
-        // itself is loaded when it is processed (12 fewer live registers in the solver loop).
-        // The solver clock starts at occasion.initial_time() and the first event is processed without advancing it
-        // (ode/mod.rs:343-347, 641-687).
-        if constexpr (M::KIND == 0) {
-            double te;
-            bool have = cur.peek_time(te);
-            bool first = true, new_segment = true, is_bnd = false;
-            double stop = 0.0;
-            int attempts = 0;
-            while (have) {
-                if (!first && te > st.t && status == ST_OK) {
-                    if (new_segment) {
-                        // next stop: the event, or the first infusion boundary in (st.t, te]  (closure.rs:103-195)
-                        while (bnd < bnd_end && __ldg(pop.bnds + bnd) <= st.t) ++bnd;
-                        stop = te;
-                        is_bnd = false;
-                        if (bnd < bnd_end) {
-                            const double b = __ldg(pop.bnds + bnd);
-                            if (b <= te) { stop = b; is_bnd = true; ++bnd; }
-                        }
-                        segment_rates<NR>(inf, st.t, c.rate);    // constant on [st.t, stop): right-continuous at st.t,
-                                                                 // left-continuous at stop (closure.rs:43-51)
-                        new_segment = false;
-                        attempts = 0;
-                    }
-                    int rc = ST_OK;
-                    if (SteppedSolver<SOLVER>::v && ++attempts > opt.max_steps) rc = ST_SOLVER_FAILURE;
-                    else rc = ode_step_once<M, SOLVER>(st, solver_mem, stop, rhs, opt, cnt);
-                    if (rc != ST_OK) { status = rc; st.t = te; new_segment = true; continue; }
-                    if (!(st.t < stop)) {
-                        if (is_bnd) st.have_k1 = false;          // RHS discontinuity: refresh dy (ode/mod.rs:568-586)
-                        new_segment = true;
-                    }
-                    continue;
-                }
-                // ---- the pending event ------------------------------------------------------------------------
-                EventRec e;
-                double t2;
-                cur.next(e, t2);
-                const int kind = ev_kind(e.meta);
-                if (kind == EV_BOLUS) {
-                    const int route = ev_index(e.meta);
-                    double amount = e.a;
-                    if constexpr (M::HAS_FA) {                       // native.rs:991-1018, at the lagged time
-                        double zx[AtLeast1<NS>::v];
-#pragma unroll
-                        for (int k = 0; k < AtLeast1<NS>::v; ++k) zx[k] = 0.0;
-                        c.zero_rate();
-                        c.refresh(te, zx);
-                        const double fa = M::fa(route, te, zx, c.p, c.cov, c.rate, c.d);
-                        if (fa != 1.0) amount *= fa;
-                    }
-                    const int dest = M::bolus_dest(route);           // native.rs:1027-1042
-                    if (dest < 0) { if (status == ST_OK) status = ST_UNSUPPORTED_INPUT_ROUTE_KIND; }
-                    add_at<AtLeast1<NS>::v>(st.y, dest, amount);
-                    st.have_k1 = false; st.h = -1.0;                 // pending_reinit (ode/mod.rs:687)
-                } else if (kind == EV_OBS) {
-                    active_rates<NR>(inf, te, c.rate);               // observation_prediction (native.rs:1044-1086)
-                    c.refresh(te, st.y);
-                    double y[AtLeast1<M::NOUT>::v];
-#pragma unroll
-                    for (int k = 0; k < AtLeast1<M::NOUT>::v; ++k) y[k] = 0.0;
-                    M::outputs(te, st.y, c.p, c.cov, c.rate, c.d, y);
-                    const double yp = pick<AtLeast1<M::NOUT>::v>(y, ev_index(e.meta));
-                    if (pred && e.obs_row >= 0) pred[(long long)e.obs_row * pred_ld] = yp;
-                    if (opt.want_ll && ev_has_value(e.meta)) {
-                        if (opt.diagonal) ll += resid_log_likelihood(opt, ev_index(e.meta), e.a, yp);
-                        else ll += obs_log_likelihood(e, yp, status);
-                    }
-                }
-                new_segment = true;                                  // lag / fa / outputs reuse c.rate as scratch
-                first = false;
-                have = cur.peek_time(te);
-            }
-            continue;
         }
 
         EventRec e;
@@ -317,6 +223,7 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                 const int dest = M::bolus_dest(route);           // native.rs:1027-1042
                 if (dest < 0) { if (status == ST_OK) status = ST_UNSUPPORTED_INPUT_ROUTE_KIND; }
                 add_at<AtLeast1<NS>::v>(x, dest, amount);
+                if constexpr (M::KIND == 0) st.have_k1 = false, st.h = -1.0;   // pending_reinit (ode/mod.rs:687)
             } else if (kind == EV_OBS) {
                 // observation_prediction (native.rs:1044-1086)
                 active_rates<NR>(inf, te, c.rate);
@@ -373,6 +280,26 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                             if (nxt == tn) break;
                         }
                     }
+                } else if constexpr (M::KIND == 0) {
+                    // ODE::run_events advance loop (ode/mod.rs:718-819)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) st.y[k] = x[k];
+                    while (tn > st.t) {
+                        while (bnd < bnd_end && __ldg(pop.bnds + bnd) <= st.t) ++bnd;
+                        double stop = tn;
+                        bool is_bnd = false;
+                        if (bnd < bnd_end) {
+                            const double b = __ldg(pop.bnds + bnd);
+                            if (b <= tn) { stop = b; is_bnd = true; ++bnd; }
+                        }
+                        segment_rates<NR>(inf, st.t, c.rate);    // constant on [st.t, stop): right-continuous at
+                                                                 // st.t, left-continuous at stop (closure.rs:43-51)
+                        const int rc = ode_advance<M, SOLVER>(st, solver_mem, stop, rhs, opt, cnt);
+                        if (rc != ST_OK) { if (status == ST_OK) status = rc; st.t = tn; break; }
+                        if (is_bnd) st.have_k1 = false;          // RHS discontinuity: refresh dy (ode/mod.rs:568-586)
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) x[k] = st.y[k];
                 }
             }
             e = en;

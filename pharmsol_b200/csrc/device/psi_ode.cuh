@@ -138,92 +138,83 @@ PSI_DEV double initial_step(F& f, double t, const double* y, const double* f0, d
     return fmin(fmin(100.0 * h0, h1), span);
 }
 
-// ONE step attempt towards tstop (st.t < tstop): accepts (st.t advances, possibly exactly onto tstop) or rejects (st.h
-// shrinks).  Returns ST_OK or ST_SOLVER_FAILURE.  The engine's flat per-lane loop calls this once per iteration, so the
-// lanes of a warp that sit in different inter-event intervals still execute the same step code together.
-template <class TAB, int N, class F>
-PSI_DEV int erk_step(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
-    const double rtol = opt.rtol, atol = opt.atol;
-    double k[TAB::S][N];
-    if (!st.have_k1) {
-        f(st.t, st.y, st.k1);
-        cnt.evals++;
-        st.have_k1 = true;
-    }
-    if (!(st.h > 0.0)) {
-        st.since_restart = 0;
-        if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
-        else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
-    }
-    const double rem = tstop - st.t;
-    const bool last = st.h >= rem;
-    const double h = last ? rem : st.h;
-#pragma unroll
-    for (int i = 0; i < N; ++i) k[0][i] = st.k1[i];
-    double ynew[N];
-#pragma unroll
-    for (int s = 1; s < TAB::S; ++s) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < s; ++j)
-                if (TAB::a(s, j) != 0.0) acc = fma(TAB::ca(s, j), k[j][i], acc);
-            ynew[i] = fma(h, acc, st.y[i]);
-        }
-        f(st.t + TAB::c(s) * h, ynew, k[s]);
-    }
-    cnt.evals += TAB::S - 1;
-    // ynew = 5th-order solution (FSAL: stage S-1 is f(t+h, ynew)).
-    // Error norm: the embedded difference sum stays in FP64 (it is a cancellation of O(1) terms down
-    // to ~tol); the per-component weight 1/sc uses the one-MUFU reciprocal and the controller runs
-    // in FP32 on the SFU: none of this steers anything but h.
-    double err2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        double e = 0.0;
-#pragma unroll
-        for (int j = 0; j < TAB::S; ++j)
-            if (TAB::e(j) != 0.0) e = fma(TAB::ce(j), k[j][i], e);
-        const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
-        const double q = (h * e) * rcp_approx(sc);
-        err2 = fma(q, q, err2);
-    }
-    if (!(err2 <= 1e300)) {
-        // non-finite error estimate: treat as a rejected step with the maximum shrink
-        cnt.rejected++;
-        st.h = h * 0.2;
-        return (st.h < 1e-14 * fmax(1.0, fabs(st.t))) ? ST_SOLVER_FAILURE : ST_OK;
-    }
-    // fac = 0.9 * err^(-1/5), err = sqrt(err2 / N)  =>  0.9 * (err2 / N)^(-1/10)
-    const float e2 = (float)err2 * (1.0f / N);
-    float fac = (e2 <= 1e-30f) ? 10.0f : 0.9f * __powf(e2, -0.1f);
-    fac = fminf(10.0f, fmaxf(0.2f, fac));
-    if (err2 <= (double)N) {
-        cnt.steps++;
-        st.t = last ? tstop : st.t + h;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { st.y[i] = ynew[i]; st.k1[i] = k[TAB::S - 1][i]; }
-        // a step clipped by tstop must not shrink the controller's step estimate
-        const double hn = h * (double)fac;
-        st.h = (last && hn < st.h) ? st.h : hn;
-        if (PSI_RESTART_REUSE && ++st.since_restart == 2) st.h_post = st.h;
-    } else {
-        cnt.rejected++;
-        st.h = h * (double)fminf(1.0f, fac);
-        if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
-    }
-    return ST_OK;
-}
-
 // Integrate from st.t to exactly tstop.  Returns ST_OK or ST_SOLVER_FAILURE.
 template <class TAB, int N, class F>
 PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
+    const double rtol = opt.rtol, atol = opt.atol;
+    double k[TAB::S][N];
     int iters = 0;
     while (st.t < tstop) {
         if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
-        const int rc = erk_step<TAB, N>(st, tstop, f, opt, cnt);
-        if (rc != ST_OK) return rc;
+        if (!st.have_k1) {
+            f(st.t, st.y, st.k1);
+            cnt.evals++;
+            st.have_k1 = true;
+        }
+        if (!(st.h > 0.0)) {
+            st.since_restart = 0;
+            if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
+            else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
+        }
+        const double rem = tstop - st.t;
+        const bool last = st.h >= rem;
+        const double h = last ? rem : st.h;
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[0][i] = st.k1[i];
+        double ynew[N];
+#pragma unroll
+        for (int s = 1; s < TAB::S; ++s) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < s; ++j)
+                    if (TAB::a(s, j) != 0.0) acc = fma(TAB::ca(s, j), k[j][i], acc);
+                ynew[i] = fma(h, acc, st.y[i]);
+            }
+            f(st.t + TAB::c(s) * h, ynew, k[s]);
+        }
+        cnt.evals += TAB::S - 1;
+        // ynew = 5th-order solution (FSAL: stage S-1 is f(t+h, ynew)).
+        // Error norm: the embedded difference sum stays in FP64 (it is a cancellation of O(1) terms down
+        // to ~tol); the per-component weight 1/sc uses the one-MUFU reciprocal and the controller runs
+        // in FP32 on the SFU: none of this steers anything but h.
+        double err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double e = 0.0;
+#pragma unroll
+            for (int j = 0; j < TAB::S; ++j)
+                if (TAB::e(j) != 0.0) e = fma(TAB::ce(j), k[j][i], e);
+            const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
+            const double q = (h * e) * rcp_approx(sc);
+            err2 = fma(q, q, err2);
+        }
+        if (!(err2 <= 1e300)) {
+            // non-finite error estimate: treat as a rejected step with the maximum shrink
+            cnt.rejected++;
+            st.h = h * 0.2;
+            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
+            continue;
+        }
+        // fac = 0.9 * err^(-1/5), err = sqrt(err2 / N)  =>  0.9 * (err2 / N)^(-1/10)
+        const float e2 = (float)err2 * (1.0f / N);
+        float fac = (e2 <= 1e-30f) ? 10.0f : 0.9f * __powf(e2, -0.1f);
+        fac = fminf(10.0f, fmaxf(0.2f, fac));
+        if (err2 <= (double)N) {
+            cnt.steps++;
+            st.t = last ? tstop : st.t + h;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { st.y[i] = ynew[i]; st.k1[i] = k[TAB::S - 1][i]; }
+            // a step clipped by tstop must not shrink the controller's step estimate
+            const double hn = h * (double)fac;
+            st.h = (last && hn < st.h) ? st.h : hn;
+            if (PSI_RESTART_REUSE && ++st.since_restart == 2) st.h_post = st.h;
+        } else {
+            cnt.rejected++;
+            st.h = h * (double)fminf(1.0f, fac);
+            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
+        }
     }
     return ST_OK;
 }

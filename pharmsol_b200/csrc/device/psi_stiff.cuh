@@ -305,13 +305,15 @@ static __constant__ double kRodasAlpha[6] = {0.0, 0.386, 0.21, 0.63, 1.0, 1.0};
 static __constant__ double kRodasD[6] = {0.25, -0.1043, 0.1035, -0.3620000000000023e-01, 0.0, 0.0};
 
 template <int N, bool TIME_DEP, class F>
-PSI_DEV int rodas4_step(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
+PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
     const double rtol = opt.rtol, atol = opt.atol;
     constexpr double g = 0.25;
     double K[6][N];
     SmallLU<N> lu;
     [[maybe_unused]] double T[N];
-    {
+    int iters = 0;
+    while (st.t < tstop) {
+        if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
         if (!st.have_k1) {
             f(st.t, st.y, st.k1);
             cnt.evals++;
@@ -396,8 +398,8 @@ PSI_DEV int rodas4_step(OdeState<N>& st, double tstop, F& f, const RunOpts& opt,
         if (bad || !(err2 <= 1e300)) {
             cnt.rejected++;
             st.h = h * 0.25;
-            if constexpr (TIME_DEP) st.have_k1 = false;      // df/dt lives in this call only: the retry re-forms it
-            return (st.h < 1e-14 * fmax(1.0, fabs(st.t))) ? ST_SOLVER_FAILURE : ST_OK;
+            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
+            continue;
         }
         // fac = 0.9 * err^(-1/4), err = sqrt(err2 / N)
         const float e2 = (float)err2 * (1.0f / N);
@@ -415,21 +417,8 @@ PSI_DEV int rodas4_step(OdeState<N>& st, double tstop, F& f, const RunOpts& opt,
         } else {
             cnt.rejected++;
             st.h = h * (double)fminf(1.0f, fac);
-            if constexpr (TIME_DEP) st.have_k1 = false;      // df/dt lives in this call only: the retry re-forms it
             if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
         }
-    }
-    return ST_OK;
-}
-
-// Integrate from st.t to exactly tstop (the one-step form above is what the engine's flat loop calls).
-template <int N, bool TIME_DEP, class F>
-PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts& opt, Counters& cnt) {
-    int iters = 0;
-    while (st.t < tstop) {
-        if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
-        const int rc = rodas4_step<N, TIME_DEP>(st, tstop, f, opt, cnt);
-        if (rc != ST_OK) return rc;
     }
     return ST_OK;
 }
