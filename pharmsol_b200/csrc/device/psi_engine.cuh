@@ -324,24 +324,27 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
     //   warp tasks   few support points (a 128-column CTA per subject would idle most lanes): the warps of a 1-D grid
     //                take (subject, 32-column chunk) tasks in order, so a CTA mixes subjects
     //   diagonal     log_likelihood_batch: thread q = subject q with parameter row q
-    const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool wt = opt.warp_tasks != 0, diag = opt.diagonal != 0;
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const long long nchunk = (ncols + 31) >> 5;
-    long long it, it_end, it_step;
-    if (wt) { it = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); it_end = nchunk * (long long)nsub; it_step = (long long)gridDim.x * wpb; }
-    else if (diag) { it = 0; it_end = (q0 < ncols) ? 1 : 0; it_step = 1; }
-    else { it = blockIdx.y; it_end = (q0 < ncols) ? nsub : 0; it_step = gridDim.y; }
-    for (; it < it_end; it += it_step) {
+    // Only ONE 32-bit value stays live across a pair (it); the bounds and everything else about the index space are
+    // recomputed from the launch parameters and special registers when needed — a pair of an ODE model runs for
+    // ~10^5 instructions under an 80-register cap, so every value held across it costs spills.
+    auto it_end = [&]() -> int {
+        if (opt.warp_tasks) return (int)((ncols + 31) >> 5) * nsub;
+        const bool in_range = (long long)blockIdx.x * blockDim.x + threadIdx.x < ncols;
+        return in_range ? (opt.diagonal ? 1 : nsub) : 0;
+    };
+    auto it_step = [&]() -> int { return opt.warp_tasks ? (int)(gridDim.x * (blockDim.x >> 5)) : (opt.diagonal ? 1 : (int)gridDim.y); };
+    int it = opt.warp_tasks ? (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : (opt.diagonal ? 0 : (int)blockIdx.y);
+    for (; it < it_end(); it += it_step()) {
+        const bool diag = opt.diagonal != 0;
         int subj;
-        long long q;
-        if (wt) {
-            subj = (int)(it / nchunk);
-            q = (it - (long long)subj * nchunk) * 32 + lane;
+        long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (opt.warp_tasks) {
+            const int nchunk = (int)((ncols + 31) >> 5);
+            subj = it / nchunk;
+            q = (long long)(it - subj * nchunk) * 32 + (threadIdx.x & 31);
             if (q >= ncols) continue;
         } else {
-            subj = diag ? (int)q0 : (int)it;
-            q = q0;
+            subj = diag ? (int)q : it;
         }
         // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
         // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
