@@ -262,3 +262,23 @@ def test_macro_style_builders_lower_to_the_same_model_as_dsl_text(ps):
                routes=["infusion(iv) -> central", "bolus(load) -> central"], drift={"central": "-ke * central"},
                diffusion={"central": "sigma"}, out={"cp": "central / v"}, particles=1000)
     assert s._model.id == ps.Equation.from_dsl(W.model_source("c5_one_cpt_sde"))._model.id and isinstance(s, ps.SDE)
+
+
+def test_rust_ffi_binds_every_declared_symbol():
+    """integration/rust/.../ffi.rs is generated from the header (scripts/gen_rust_ffi.py): it must be up to date and must
+    declare every function of include/pharmsol_cuda.h, with pointer-to-pointer arguments spelled out."""
+    import re
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from pharmsol_b200 import _lib
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_rust_ffi.py"), "--check"])
+    assert r.returncode == 0, "integration/rust/src/simulator/cuda/ffi.rs is stale: run scripts/gen_rust_ffi.py"
+    text = open(os.path.join(ROOT, "integration", "rust", "src", "simulator", "cuda", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (pharmsol_[a-z0-9_]+)\(", text))
+    assert bound == set(_lib.declared_symbols())
+    assert "out_full_peers: *const *mut f64" in text and "dev_out: *mut *mut f64" in text and "device_ids: *const i32" in text
+    # the glue uses only functions the FFI block declares
+    glue = open(os.path.join(ROOT, "integration", "rust", "src", "simulator", "cuda", "mod.rs")).read()
+    used = set(re.findall(r"ffi::(pharmsol_[a-z0-9_]+)", glue))
+    assert used and used <= bound, used - bound
