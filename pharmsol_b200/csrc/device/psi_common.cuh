@@ -69,6 +69,10 @@ struct PairCtx {
     double rate[AtLeast1<M::NROUTE>::v];
     const PopView* pop;
     int occ;
+    // timeline program of the pair's subject: record q lives at prog[q - prog_first] — the global array (prog_first = 0)
+    // or the CTA's shared-memory copy of this subject's records (psi_engine.cuh psi_kernel_body)
+    const EventRec* prog;
+    int prog_first;
 
     // SharedNativeModel::refresh_derived (dsl/native.rs:828-857): covariates at `t`, then derive.
     PSI_DEV void refresh(double t, const double* x) {
@@ -244,6 +248,19 @@ PSI_DEV EventRec load_event(const EventRec* __restrict__ p) {
     const double2 a = __ldg(reinterpret_cast<const double2*>(p));
     const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
     const double2 c = __ldg(reinterpret_cast<const double2*>(p) + 2);
+    e.time = a.x; e.a = a.y; e.b = b.x; e.w = b.y; e.sigma = c.x;
+    const long long m = __double_as_longlong(c.y);
+    e.meta = (int)(m & 0xffffffffLL);
+    e.obs_row = (int)(m >> 32);
+    return e;
+}
+
+// The same record through a generic pointer (the shared-memory copy of a subject's timeline program).
+PSI_DEV EventRec load_event_any(const EventRec* p) {
+    EventRec e;
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    const double2 c = *(reinterpret_cast<const double2*>(p) + 2);
     e.time = a.x; e.a = a.y; e.b = b.x; e.w = b.y; e.sigma = c.x;
     const long long m = __double_as_longlong(c.y);
     e.meta = (int)(m & 0xffffffffLL);
