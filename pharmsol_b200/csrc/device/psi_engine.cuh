@@ -332,10 +332,14 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
     // Only ONE 32-bit value stays live across a pair (it); the bounds and everything else about the index space are
     // recomputed from the launch parameters and special registers when needed — a pair of an ODE model runs for
     // ~10^5 instructions under an 80-register cap, so every value held across it costs spills.
+    // Closed-form models without lag stage the subject's timeline program in shared memory (below): then EVERY thread of
+    // the CTA walks the subject loop — also the ones past the last column — because the staging uses block barriers.
+    constexpr bool kStaged = (M::KIND == 1 && !M::HAS_LAG);
     auto it_end = [&]() -> int {
         if (opt.warp_tasks) return (int)((ncols + 31) >> 5) * nsub;
+        if (opt.diagonal) return ((long long)blockIdx.x * blockDim.x + threadIdx.x < ncols) ? 1 : 0;
         const bool in_range = (long long)blockIdx.x * blockDim.x + threadIdx.x < ncols;
-        return in_range ? (opt.diagonal ? 1 : nsub) : 0;
+        return (in_range || kStaged) ? nsub : 0;
     };
     auto it_step = [&]() -> int { return opt.warp_tasks ? (int)(gridDim.x * (blockDim.x >> 5)) : (opt.diagonal ? 1 : (int)gridDim.y); };
     int it = opt.warp_tasks ? (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : (opt.diagonal ? 0 : (int)blockIdx.y);
@@ -351,21 +355,14 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         } else {
             subj = diag ? (int)q : it;
         }
-        // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
-        // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
-        const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
-        PairCtx<M> c;
-#pragma unroll
-        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
-        M::prologue(c.p);
         // Closed-form models: in the matrix index space a CTA is 128 columns of ONE subject, so its threads execute the
         // same timeline program.  Stage it in shared memory once per CTA (one coalesced copy) instead of letting every warp
         // chase the records through L1 / L2 one dependent load at a time (ncu on C1 before this: 8.7 long-scoreboard
         // stall cycles per issued instruction, L1 hit rate 76 %).  Longer programs stay in global memory.
-        c.prog = pop.prog;
-        c.prog_first = 0;
-        if constexpr (M::KIND == 1 && !M::HAS_LAG) {
-            if (!opt.warp_tasks && !diag) {
+        [[maybe_unused]] const EventRec* prog_ptr = pop.prog;
+        [[maybe_unused]] int prog_first = 0;
+        if constexpr (kStaged) {
+            if (!opt.warp_tasks && !diag) {                         // uniform over the CTA: every thread takes the barriers
                 __shared__ double2 sprog[PSI_PROG_STAGE * 3];
                 const int p0 = __ldg(pop.prog_offsets + __ldg(pop.occ_offsets + subj));
                 const int p1 = __ldg(pop.prog_offsets + __ldg(pop.occ_offsets + subj + 1));
@@ -377,12 +374,22 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
 #else
                     for (int i = threadIdx.x; i < (p1 - p0) * 3; i += blockDim.x) sprog[i] = __ldg(src + i);
 #endif
-                    c.prog = reinterpret_cast<const EventRec*>(sprog);
-                    c.prog_first = p0;
+                    prog_ptr = reinterpret_cast<const EventRec*>(sprog);
+                    prog_first = p0;
                 }
                 __syncthreads();
+                if (q >= ncols) continue;                           // a thread past the last column only helped to stage
             }
         }
+        // work-balanced warps: slot q -> column col_perm[q] (columns ordered by probed step counts); the
+        // parameter loads become a gather (P loads per pair, nothing against hundreds of solver steps)
+        const long long j = out.col_perm ? (long long)__ldg(out.col_perm + q) : q;
+        PairCtx<M> c;
+#pragma unroll
+        for (int k = 0; k < M::NP; ++k) c.p[k] = __ldg(spp + (long long)k * spp_ld + j);
+        M::prologue(c.p);
+        c.prog = prog_ptr;
+        c.prog_first = prog_first;
         int status = ST_OK;
         double* pred = (opt.want_pred && out.pred && !diag) ? out.pred + j : nullptr;
         const unsigned int work0 = cnt.steps + cnt.rejected;
