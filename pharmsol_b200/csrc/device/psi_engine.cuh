@@ -318,17 +318,19 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
 // Kernel entry: grid = (ceil(ncols/128), min(nsub, 65535)), block = 128.
 // spp is SoA: spp[k*spp_ld + j]; psi is column-major: out.ll[i + j*out.ld_ll].
 // ---------------------------------------------------------------------------------------------
-template <class M, int SOLVER>
-__device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
+template <class M, int SOLVER, int MODE>
+__device__ __forceinline__ void psi_pair_loop(const PopView& pop, const double* __restrict__ spp, long long ncols,
                                                 long long spp_ld, const RunOpts& opt, const OutView& out) {
     const int nsub = (opt.nsub_limit > 0 && opt.nsub_limit < pop.nsub) ? opt.nsub_limit : pop.nsub;
     Counters cnt;
-    // ONE inlined copy of the pair code serves the three index spaces (a copy per mode tripled the code and the register
-    // allocation is the maximum over all of them):
-    //   matrix       blockIdx.x * blockDim.x + threadIdx.x = column slot, blockIdx.y strides over subjects
-    //   warp tasks   few support points (a 128-column CTA per subject would idle most lanes): the warps of a 1-D grid
-    //                take (subject, 32-column chunk) tasks in order, so a CTA mixes subjects
-    //   diagonal     log_likelihood_batch: thread q = subject q with parameter row q
+    // MODE (compile time; psi_kernel_body picks the instantiation): the three index spaces of a launch
+    //   0 matrix       blockIdx.x * blockDim.x + threadIdx.x = column slot, blockIdx.y strides over subjects
+    //   1 warp tasks   few support points (a 128-column CTA per subject would idle most lanes): the warps of a 1-D grid
+    //                  take (subject, 32-column chunk) tasks in order, so a CTA mixes subjects
+    //   2 diagonal     log_likelihood_batch: thread q = subject q with parameter row q
+    // One source, three instantiations: with the mode a run-time value the Dopri5 kernel of C2 executed 5.8 % more
+    // instructions per launch than with a dedicated copy per mode (ncu, profiles/r02_tuning.md).
+    constexpr bool kWarpTasks = MODE == 1, kDiagonal = MODE == 2;
     // Only ONE 32-bit value stays live across a pair (it); the bounds and everything else about the index space are
     // recomputed from the launch parameters and special registers when needed — a pair of an ODE model runs for
     // ~10^5 instructions under an 80-register cap, so every value held across it costs spills.
@@ -336,18 +338,18 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
     // the CTA walks the subject loop — also the ones past the last column — because the staging uses block barriers.
     constexpr bool kStaged = (M::KIND == 1 && !M::HAS_LAG);
     auto it_end = [&]() -> int {
-        if (opt.warp_tasks) return (int)((ncols + 31) >> 5) * nsub;
-        if (opt.diagonal) return ((long long)blockIdx.x * blockDim.x + threadIdx.x < ncols) ? 1 : 0;
+        if (kWarpTasks) return (int)((ncols + 31) >> 5) * nsub;
+        if (kDiagonal) return ((long long)blockIdx.x * blockDim.x + threadIdx.x < ncols) ? 1 : 0;
         const bool in_range = (long long)blockIdx.x * blockDim.x + threadIdx.x < ncols;
         return (in_range || kStaged) ? nsub : 0;
     };
-    auto it_step = [&]() -> int { return opt.warp_tasks ? (int)(gridDim.x * (blockDim.x >> 5)) : (opt.diagonal ? 1 : (int)gridDim.y); };
-    int it = opt.warp_tasks ? (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : (opt.diagonal ? 0 : (int)blockIdx.y);
+    auto it_step = [&]() -> int { return kWarpTasks ? (int)(gridDim.x * (blockDim.x >> 5)) : (kDiagonal ? 1 : (int)gridDim.y); };
+    int it = kWarpTasks ? (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : (kDiagonal ? 0 : (int)blockIdx.y);
     for (; it < it_end(); it += it_step()) {
-        const bool diag = opt.diagonal != 0;
+        const bool diag = kDiagonal;
         int subj;
         long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        if (opt.warp_tasks) {
+        if (kWarpTasks) {
             const int nchunk = (int)((ncols + 31) >> 5);
             subj = it / nchunk;
             q = (long long)(it - subj * nchunk) * 32 + (threadIdx.x & 31);
@@ -362,7 +364,7 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         [[maybe_unused]] const EventRec* prog_ptr = pop.prog;
         [[maybe_unused]] int prog_first = 0;
         if constexpr (kStaged) {
-            if (!opt.warp_tasks && !diag) {                         // uniform over the CTA: every thread takes the barriers
+            if (!kWarpTasks && !diag) {                         // uniform over the CTA: every thread takes the barriers
                 __shared__ double2 sprog[PSI_PROG_STAGE * 3];
                 const int p0 = __ldg(pop.prog_offsets + __ldg(pop.occ_offsets + subj));
                 const int p1 = __ldg(pop.prog_offsets + __ldg(pop.occ_offsets + subj + 1));
@@ -414,6 +416,14 @@ __device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double
         }
     }
     flush_counters(out, cnt);
+}
+
+template <class M, int SOLVER>
+__device__ __forceinline__ void psi_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
+                                                long long spp_ld, const RunOpts& opt, const OutView& out) {
+    if (opt.warp_tasks) psi_pair_loop<M, SOLVER, 1>(pop, spp, ncols, spp_ld, opt, out);
+    else if (opt.diagonal) psi_pair_loop<M, SOLVER, 2>(pop, spp, ncols, spp_ld, opt, out);
+    else psi_pair_loop<M, SOLVER, 0>(pop, spp, ncols, spp_ld, opt, out);
 }
 
 template <class M, int SOLVER>
