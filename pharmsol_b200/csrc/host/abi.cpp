@@ -893,7 +893,9 @@ static int32_t predictions_shard(Ctx& c, Model& m, Population& pop, const psi::P
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
     c.status_batch = false;
     const int64_t nobs = pop.flat.nobs_total;
-    int64_t chunk = std::max<int64_t>(128, ((256ll << 20) / std::max<int64_t>(1, nobs * 8)) / 128 * 128);
+    int64_t budget = 256ll << 20;
+    if (const char* kb = std::getenv("PHARMSOL_B200_PRED_CHUNK_KB")) budget = std::max<int64_t>(1, std::atoll(kb)) << 10;      // test knob
+    int64_t chunk = std::max<int64_t>(128, (budget / std::max<int64_t>(1, nobs * 8)) / 128 * 128);
     chunk = std::min<int64_t>(chunk, (ncols + 127) / 128 * 128);
     c.spp_rows.reserve((size_t)ncols * np * 8);
     c.spp_soa.reserve((size_t)ncols * np * 8);

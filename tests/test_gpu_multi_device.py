@@ -121,3 +121,31 @@ def test_wide_model_support_point_transpose(ps, oracle):
     pred, _ = eq.predictions_matrix(data, spp)
     want = np.stack([100.0 * np.exp(-spp[:, 0] * t) / spp[:, 31] for t in (1.0, 3.0)])
     assert np.max(np.abs(pred - want) / np.abs(want)) <= 1e-13
+
+
+def test_predictions_are_chunked_through_two_device_buffers(ps, monkeypatch):
+    """estimate_predictions for a large grid is produced in column chunks through two device buffers (a C3-sized
+    shard would otherwise need 5 GB at once).  Force tiny chunks (128 columns) and compare with the one-piece result,
+    on one device and on the two-shard context."""
+    from benches import harness as H, workloads as W
+    w = W.make("c3", nsub=20, nspp=1100)
+    eq, data, ems = H.product_objects(w)
+    want, offs = eq.predictions_matrix(data, w["support_points"])
+    monkeypatch.setenv("PHARMSOL_B200_PRED_CHUNK_KB", "64")          # 200 rows x 8 B -> 40 columns -> rounded up to 128
+    got, _ = eq.predictions_matrix(data, w["support_points"])
+    assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True)
+    eq2, data2, _ = H.product_objects(w, device=[0, 0])
+    got2, _ = eq2.predictions_matrix(data2, w["support_points"])
+    assert np.array_equal(got2, want, equal_nan=True)
+
+
+def test_few_columns_fall_back_to_the_first_device_and_uneven_shards(ps):
+    """Fewer than 32 columns per device: the call runs on device_ids[0] alone; 3 shards of an odd column count split 34/34/32."""
+    from benches import harness as H, workloads as W
+    w = W.make("c1", nsub=9, nspp=100)
+    eq, data, ems = H.product_objects(w)
+    ref = ps.log_likelihood_matrix(eq, data, w["support_points"], ems)
+    eq3, data3, ems3 = H.product_objects(w, device=[0, 0, 0])
+    assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"], ems3), ref)
+    assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"][:40], ems3), ref[:, :40])      # 40 < 3 * 32
+    assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"][:1], ems3), ref[:, :1])        # latency path
