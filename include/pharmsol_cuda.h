@@ -9,8 +9,9 @@
  *     `PharmsolError` / `ErrorModelError` variant (src/error/mod.rs:14-49);
  *   - out-parameters by pointer; host buffers are caller-owned; device buffers live behind the
  *     opaque handles and are freed by the matching *_destroy / *_free;
- *   - handles are safe to use from several host threads (one internal lock per context), matching
- *     `Equation: Sync` (src/simulator/equation/mod.rs:377);
+ *   - handles are safe to use from several host threads, matching `Equation: Sync`
+ *     (src/simulator/equation/mod.rs:377); concurrent host-buffer calls on one context run on separate
+ *     stream "lanes" (pharmsol_cuda_ctx_num_lanes) instead of queueing behind one lock;
  *   - nothing here ever aborts or traps: the reference's `panic!`s on this path (imaginary roots,
  *     missing covariates, particle-filter likelihood errors) become status codes;
  *   - there is NO CPU fallback: every compute entry point fails with PCU_ERR_CUDA when no sm_100
@@ -116,6 +117,11 @@ int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out);
 int32_t pharmsol_cuda_ctx_create_multi(const int32_t* device_ids, int32_t n_dev, pcu_ctx** out);
 int32_t pharmsol_cuda_ctx_num_devices(pcu_ctx* ctx);
 int32_t pharmsol_cuda_ctx_device_id(pcu_ctx* ctx, int32_t k);             /* -1 if k is out of range */
+/* Concurrency of one context (`Equation: Sync`: one shared handle is used from all rayon threads, equation/mod.rs:377): the
+ * host-buffer calls of a single-device context do not queue behind one lock — a caller that finds the context busy takes
+ * (or creates, up to 4) another "lane" on the same device with its own streams, staging and status buffers, so matrices
+ * requested by different host threads overlap on the GPU.  Returns how many lanes exist (>= 1). */
+int32_t pharmsol_cuda_ctx_num_lanes(pcu_ctx* ctx);
 void    pharmsol_cuda_ctx_destroy(pcu_ctx* ctx);
 /* message of the last failure on this thread (valid until the next failing call on the thread) */
 const char* pharmsol_cuda_last_error_message(void);

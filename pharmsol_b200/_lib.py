@@ -73,6 +73,7 @@ def lib():
         "pharmsol_cuda_ctx_create_multi": (i32, [P(i32), i32, P(vp)]),
         "pharmsol_cuda_ctx_num_devices": (i32, [vp]),
         "pharmsol_cuda_ctx_device_id": (i32, [vp, i32]),
+        "pharmsol_cuda_ctx_num_lanes": (i32, [vp]),
         "pharmsol_cuda_ctx_destroy": (None, [vp]),
         "pharmsol_cuda_last_error_message": (cs, []),
         "pharmsol_cuda_launch_count": (i64, [vp]),
@@ -207,6 +208,10 @@ class Context:
     @property
     def num_devices(self):
         return lib().pharmsol_cuda_ctx_num_devices(self.ptr)
+
+    @property
+    def num_lanes(self):
+        return lib().pharmsol_cuda_ctx_num_lanes(self.ptr)
 
     def close(self):
         if self.ptr:

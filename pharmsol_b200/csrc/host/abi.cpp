@@ -22,6 +22,13 @@ struct pcu_ctx {
     int ndev() const { return 1 + (int)more.size(); }
     Ctx& dev(int k) { return k == 0 ? c : *more[(size_t)k - 1]; }
     bool peer_enabled = false;
+    // Host-buffer calls from several host threads (rayon over subjects: `Equation: Sync`, equation/mod.rs:377) do not queue
+    // behind one lock: a single-device context grows up to kMaxLanes extra Ctx bundles on the same device (own streams,
+    // events, staging and status buffers), and a call takes whichever is free, so small matrices from different threads
+    // overlap on the GPU instead of running one after the other.
+    static constexpr int kMaxLanes = 4;
+    std::vector<std::unique_ptr<Ctx>> lanes;
+    std::mutex lanes_mu;
 };
 struct pcu_model { Model m; };
 struct pcu_subject_builder { SubjectBuilder b; std::string error; explicit pcu_subject_builder(const char* id) : b(id) {} };
@@ -139,6 +146,41 @@ static void init_ctx(Ctx& c, int32_t device) {
     cuda_check(cudaMallocHost((void**)&c.small_host, Ctx::kSmallIn + Ctx::kSmallOut), "cudaMallocHost");
 }
 
+struct LaneLock {
+    Ctx* c = nullptr;
+    std::unique_lock<std::mutex> lk;
+};
+// The primary bundle if it is free, else a free (or new) lane, else wait for the primary.
+static LaneLock acquire_lane(pcu_ctx* ctx) {
+    LaneLock r;
+    r.lk = std::unique_lock<std::mutex>(ctx->c.mu, std::try_to_lock);
+    if (r.lk.owns_lock()) { r.c = &ctx->c; return r; }
+    if (ctx->ndev() == 1) {
+        std::lock_guard<std::mutex> g(ctx->lanes_mu);
+        for (auto& l : ctx->lanes) {
+            std::unique_lock<std::mutex> lk(l->mu, std::try_to_lock);
+            if (lk.owns_lock()) { r.c = l.get(); r.lk = std::move(lk); return r; }
+        }
+        if ((int)ctx->lanes.size() < pcu_ctx::kMaxLanes) {
+            std::unique_ptr<Ctx> l(new Ctx());
+            init_ctx(*l, ctx->c.device);
+            r.lk = std::unique_lock<std::mutex>(l->mu);
+            r.c = l.get();
+            ctx->lanes.push_back(std::move(l));
+            return r;
+        }
+    }
+    r.lk = std::unique_lock<std::mutex>(ctx->c.mu);
+    r.c = &ctx->c;
+    return r;
+}
+static void publish_lane_stats(pcu_ctx* ctx, const Ctx& lane) {
+    if (&lane == &ctx->c) return;
+    std::lock_guard<std::mutex> g(ctx->lanes_mu);
+    ctx->c.last_kernel_ms = lane.last_kernel_ms;
+    for (int k = 0; k < 4; ++k) ctx->c.last_counters[k] = lane.last_counters[k];
+}
+
 int32_t pharmsol_cuda_ctx_create(int32_t device, pcu_ctx** out) {
     return guarded([&] {
         if (!out) return (int32_t)PCU_ERR_INVALID_ARGUMENT;
@@ -185,6 +227,11 @@ int32_t pharmsol_cuda_ctx_create_multi(const int32_t* device_ids, int32_t n_dev,
     });
 }
 int32_t pharmsol_cuda_ctx_num_devices(pcu_ctx* ctx) { return ctx ? ctx->ndev() : 0; }
+int32_t pharmsol_cuda_ctx_num_lanes(pcu_ctx* ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> g(ctx->lanes_mu);
+    return 1 + (int32_t)ctx->lanes.size();
+}
 int32_t pharmsol_cuda_ctx_device_id(pcu_ctx* ctx, int32_t k) { return (ctx && k >= 0 && k < ctx->ndev()) ? ctx->dev(k).device : -1; }
 void pharmsol_cuda_ctx_destroy(pcu_ctx* ctx) { delete ctx; }
 const char* pharmsol_cuda_last_error_message(void) { return last_error().c_str(); }
@@ -192,6 +239,8 @@ int64_t pharmsol_cuda_launch_count(pcu_ctx* ctx) {
     if (!ctx) return 0;
     int64_t n = 0;
     for (int k = 0; k < ctx->ndev(); ++k) n += ctx->dev(k).launches;
+    std::lock_guard<std::mutex> g(ctx->lanes_mu);
+    for (auto& l : ctx->lanes) n += l->launches;
     return n;
 }
 double pharmsol_cuda_last_kernel_ms(pcu_ctx* ctx) { return ctx ? ctx->c.last_kernel_ms : 0.0; }
@@ -754,13 +803,11 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
             throw PharmsolError(PCU_ERR_OTHER, "model `" + m->m.cm.name + "` expects " + std::to_string(m->m.cm.parameters.size()) +
                                                    " parameter value(s), got " + std::to_string(np));
         }
-        std::lock_guard<std::mutex> lk(ctx->c.mu);
-        Ctx& c = ctx->c;
-        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-        c.status_batch = false;      // a host-buffer call resets and reads the status itself
         const int64_t nsub = pop->p.flat.nsub;
         if (nspp == 0 || nsub == 0) { if (code) *code = 0; if (pair) *pair = -1; return (int32_t)PCU_OK; }
         if (use_all_devices(ctx, nspp)) {
+            std::lock_guard<std::mutex> lk(ctx->c.mu);
+            cuda_check(cudaSetDevice(ctx->c.device), "cudaSetDevice");
             if ((int)pop->p.replicas.size() + 1 != ctx->ndev()) throw PharmsolError(PCU_ERR_OTHER, "population was created for another context (device list differs)");
             const int64_t per = shard_columns(nspp, ctx->ndev());
             return for_each_device(ctx, [&](int k, int32_t* scode, int64_t* spair) {
@@ -769,6 +816,11 @@ static int32_t matrix_host(pcu_ctx* ctx, pcu_model* m, pcu_population* pop, cons
                 return matrix_host_shard(ctx->dev(k), m->m, pop->p, pop->p.view_on(k), spp + lo * np, hi - lo, np, out + lo * nsub, lo, exponentiate, scode, spair);
             }, code, pair);
         }
+        LaneLock lane = acquire_lane(ctx);      // one of up to 1 + kMaxLanes bundles on the device: concurrent callers overlap
+        Ctx& c = *lane.c;
+        struct Publish { pcu_ctx* ctx; Ctx& c; ~Publish() { publish_lane_stats(ctx, c); } } publish{ctx, c};
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+        c.status_batch = false;      // a host-buffer call resets and reads the status itself
         if (c.small_host && (size_t)nspp * np * 8 <= Ctx::kSmallIn && (size_t)nsub * nspp * 8 <= Ctx::kSmallOut) {
             // Latency-bound call (an optimiser's cost function: one or a few support points).  Support points are
             // transposed on the host into pinned memory; results and status come back through pinned memory with one

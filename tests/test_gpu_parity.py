@@ -775,6 +775,37 @@ def test_concurrent_host_threads_share_one_equation(ps, H, W):
     assert not errs, errs
     for k in range(4):
         assert np.array_equal(out[k], serial[k])
+    # the concurrent callers did not queue behind one lock: the context grew extra stream lanes
+    assert eq._ctx().num_lanes >= 2
+
+
+def test_concurrent_callers_with_errors_keep_their_own_status(ps):
+    """Lanes carry their own error word: a failing matrix on one thread must not leak its status into a clean matrix
+    evaluated at the same time on another thread (matrix.rs:96-104 is per call)."""
+    import threading
+    eq = ps.Equation.from_dsl(FX.kernel_dsl("two_compartments"))
+    ops = [("bolus", 0.0, 100.0, "0"), ("observation", 1.0, 50.0, "0"), ("observation", 2.0, 30.0, "0")]
+    data = ps.Data([ps.Subject(f"s{i}", ops) for i in range(64)])
+    ems = ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(0.1, 0.1, 0, 0), 0.0))
+    good = np.tile(np.array([[0.1, 3.0, 1.0, 1.0]]), (700, 1))
+    bad = good.copy()
+    bad[555] = [1.0, -3.0, 1.5, 1.0]        # imaginary roots
+    ref = ps.log_likelihood_matrix(eq, data, good, ems)
+    res = {}
+
+    def run(name, spp):
+        for _ in range(20):
+            try:
+                res[name] = ("ok", ps.log_likelihood_matrix(eq, data, spp, ems))
+            except ps.PharmsolError as e:
+                res[name] = ("err", e.code, e.pair)
+    ts = [threading.Thread(target=run, args=("good", good)), threading.Thread(target=run, args=("bad", bad))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert res["good"][0] == "ok" and np.array_equal(res["good"][1], ref)
+    assert res["bad"] == ("err", 12, 555 * 64)
 
 
 def test_solver_failure_is_a_status_not_a_hang(ps):
