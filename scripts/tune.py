@@ -20,6 +20,8 @@ ap.add_argument("--nspp", type=int, default=0)
 ap.add_argument("--tol", type=float, default=1e-6)
 ap.add_argument("--solver", default="")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--sde-fp64", action="store_true", help="SDE: FP64 Box-Muller noise instead of the FP32 default")
+ap.add_argument("--particles", type=int, default=1000)
 ap.add_argument("--variants", nargs="+", default=["|128"])
 args = ap.parse_args()
 
@@ -41,6 +43,8 @@ for v in args.variants:
     eq, data, ems = H.product_objects(w, device=0)
     if w["kind"] == "ode":
         eq.with_solver(getattr(ps.OdeSolver, args.solver or cfg["solver"])).with_tolerances(args.tol, args.tol)
+    if w["kind"] == "sde":
+        eq.with_particles(args.particles).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.ReferenceAdaptive).with_noise_precision(args.sde_fp64)
     job = ps.ResidentPsi(eq, data, w["support_points"], ems, device=dev, shard=False)
     for _ in range(2):
         job.launch()
