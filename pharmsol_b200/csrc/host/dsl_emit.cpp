@@ -1021,8 +1021,11 @@ CompiledModel compile_model(const ModelAst& ast_in) {
         int min_blocks = 6;
         if (ast.kind == ModelKind::Analytical && !cm.has_lag) {
             const int ak = cm.analytical_kernel;          // 0-3 one compartment, 4-7 two compartments, 8-11 three
-            if (ak >= 0 && ak <= 3) min_blocks = 10;
-            else if (ak >= 4 && ak <= 7) min_blocks = 8;
+            // the 48-register cap is for the plain kernels only: derive blocks, covariates or bioavailability
+            // expressions need room, and spilling them would cost more than the occupancy buys
+            const bool plain = !cm.has_derive && cm.covariates.empty() && !cm.has_fa;
+            if (ak >= 0 && ak <= 3) min_blocks = plain ? 10 : 8;
+            else if (ak >= 4 && ak <= 7) min_blocks = plain ? 8 : 6;
         }
         H << "    static constexpr int MIN_BLOCKS = " << min_blocks << ";\n";
     }

@@ -19,7 +19,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pharmsol_b200", "csrc")
-BUILD = os.path.join(HERE, "_build")
+# HOSTSIM_SANITIZE=1: build the host double with AddressSanitizer + UBSan (own build directory) and run it under
+#   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_hostsim.py
+# — the bounds / UB check of the device source that compute-sanitizer would give on a GPU (it is closed on this pool).
+SANITIZE = bool(os.environ.get("HOSTSIM_SANITIZE"))
+BUILD = os.path.join(HERE, "_build_san" if SANITIZE else "_build")
+SAN_FLAGS = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if SANITIZE else []
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 DSLC = os.path.join(ROOT, "pharmsol_b200", "_build", "dslc")
 
@@ -43,7 +48,7 @@ def _common_objects():
     for src in (os.path.join(host, "data.cpp"), os.path.join(host, "dsl_parse.cpp"), os.path.join(host, "dsl_emit.cpp"), os.path.join(HERE, "hostsim_api.cpp")):
         obj = os.path.join(BUILD, os.path.basename(src) + ".o")
         if _newer(obj, [src] + hdrs):
-            _run([GXX, "-std=c++17", "-O1", "-fPIC", "-I", host, "-I", os.path.join(CSRC, "device"), "-c", src, "-o", obj])
+            _run([GXX, "-std=c++17", "-O1", "-fPIC"] + SAN_FLAGS + ["-I", host, "-I", os.path.join(CSRC, "device"), "-c", src, "-o", obj])
         objs.append(obj)
     return objs
 
@@ -67,7 +72,7 @@ def build_module(dsl_source: str) -> str:
             f.write(_run([DSLC, pm]))
     objs = _common_objects()
     if _newer(so, [cu, os.path.join(HERE, "cuda_shim.h")] + dev_hdrs + objs):
-        _run([GXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-include", os.path.join(HERE, "cuda_shim.h"), "-I", dev, cu] + objs + ["-ldl", "-o", so + ".tmp"])
+        _run([GXX, "-std=c++17", "-O1" if SANITIZE else "-O2", "-fPIC", "-shared", "-w"] + SAN_FLAGS + ["-include", os.path.join(HERE, "cuda_shim.h"), "-I", dev, cu] + objs + ["-ldl", "-o", so + ".tmp"])
         os.replace(so + ".tmp", so)
     return so
 
