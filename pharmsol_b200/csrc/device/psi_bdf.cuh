@@ -92,37 +92,60 @@ PSI_DEV double bdf_rms(const double* v, const double* scale_y, double rtol, doub
     return sqrt(s * (1.0 / N));
 }
 
-// R[i][j] = prod_{m<=i} M[m][j], M[0][*] = 1, M[i>=1][j>=1] = (i - 1 - factor j) / i, M[i>=1][0] = 0
-PSI_DEV void bdf_compute_R(int order, double factor, double R[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1]) {
-    for (int j = 0; j <= order; ++j) R[0][j] = 1.0;
-    for (int i = 1; i <= order; ++i) {
-        R[i][0] = 0.0;
-        for (int j = 1; j <= order; ++j) R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * (double)j) / (double)i);
-    }
-}
-// Rescale the differences for a step-size change h -> factor * h:  D[:k+1] <- (R U)^T D[:k+1]
+// Step-size change h -> factor * h:  D[:k+1] <- (R U)^T D[:k+1]  with
+//   R[i][j] = prod_{m=1..i} (m - 1 - factor j) / m   (R[0][j] = 1, R[i>=1][0] = 0),   U = R(factor = 1).
+// U depends on nothing but the order: it is a constant table (kBdfU, computed once below).  R is never stored: with
+// W = R^T D (column j of R is generated by its recurrence while it is consumed) the update is D_new = U^T W, so the
+// scratch is (order+1) x N doubles instead of three 6 x 6 matrices — the first version kept 1.8 KB of dynamically indexed
+// local memory per thread and ran 65x slower per step than the register-resident Dopri5 (profiles/r02_tuning.md).
+// kBdfU[i][j] = prod_{m=1..i} (m - 1 - j) / m = (-1)^i C(j, i): upper triangular (the factor m - 1 - j vanishes at m = j + 1)
+static __constant__ double kBdfU[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1] = {
+    {1, 1, 1, 1, 1, 1},
+    {0, -1, -2, -3, -4, -5},
+    {0, 0, 1, 3, 6, 10},
+    {0, 0, 0, -1, -4, -10},
+    {0, 0, 0, 0, 1, 5},
+    {0, 0, 0, 0, 0, -1}};
+static __constant__ double kBdfInv[BDF_MAX_ORDER + 1] = {0.0, 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2};
+// Out of line on purpose: it is called from five places of the step loop and every inlined copy would carry its own scratch.
 template <int N>
-PSI_DEV void bdf_change_D(BdfState<N>& B, int order, double factor) {
-    double R[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1], U[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1], RU[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1];
-    bdf_compute_R(order, factor, R);
-    bdf_compute_R(order, 1.0, U);
-    for (int i = 0; i <= order; ++i)
-        for (int j = 0; j <= order; ++j) {
-            double s = 0.0;
-            for (int m = 0; m <= order; ++m) s = fma(R[i][m], U[m][j], s);
-            RU[i][j] = s;
-        }
-    double T[BDF_MAX_ORDER + 1][N];
-    for (int j = 0; j <= order; ++j)
+__device__ __noinline__ void bdf_change_D(BdfState<N>& B, int order, double factor) {
+    double W[BDF_MAX_ORDER + 1][N];
+    // W[j] = sum_i R[i][j] D[i]
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-            double s = 0.0;
-            for (int i = 0; i <= order; ++i) s = fma(RU[i][j], B.D[i][q], s);
-            T[j][q] = s;
-        }
-    for (int j = 0; j <= order; ++j)
+    for (int j = 0; j <= BDF_MAX_ORDER; ++j) {
+        if (j > order) break;
+        double r = 1.0;                                   // R[0][j]
+        double acc[N];
 #pragma unroll
-        for (int q = 0; q < N; ++q) B.D[j][q] = T[j][q];
+        for (int q = 0; q < N; ++q) acc[q] = B.D[0][q];
+#pragma unroll
+        for (int i = 1; i <= BDF_MAX_ORDER; ++i) {
+            if (i > order) break;
+            r = (j == 0) ? 0.0 : r * (((double)(i - 1) - factor * (double)j) * kBdfInv[i]);
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[q] = fma(r, B.D[i][q], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) W[j][q] = acc[q];
+    }
+    // D[j] = sum_m U[m][j] W[m]
+#pragma unroll
+    for (int j = 0; j <= BDF_MAX_ORDER; ++j) {
+        if (j > order) break;
+        double acc[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc[q] = 0.0;
+#pragma unroll
+        for (int m = 0; m <= BDF_MAX_ORDER; ++m) {
+            if (m > order || m > j) break;                // U[m][j] = 0 for m > j
+            const double u = kBdfU[m][j];
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[q] = fma(u, W[m][q], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) B.D[j][q] = acc[q];
+    }
 }
 
 template <int N, class F>
@@ -249,7 +272,9 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
                         const double dy_norm = bdf_rms<N>(dy, ypred, rtol, atol);
                         const bool have_rate = dy_norm_old >= 0.0;
                         const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
-                        if (have_rate && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+                        double rate_pow = rate;                      // rate^(NEWTON_MAXITER - k)
+                        for (int e = 1; e < NEWTON_MAXITER - k; ++e) rate_pow *= rate;
+                        if (have_rate && (rate >= 1.0 || rate_pow / (1.0 - rate) * dy_norm > newton_tol)) break;
 #pragma unroll
                         for (int i = 0; i < N; ++i) { ynew[i] += dy[i]; d[i] += dy[i]; }
                         if (dy_norm == 0.0 || (have_rate && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
@@ -278,7 +303,7 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
             error_norm = bdf_rms<N>(err, scale_y, rtol, atol);
             if (!(error_norm <= 1.0)) {
                 cnt.rejected++;
-                const double factor = (error_norm == error_norm) ? fmax(MIN_FACTOR, safety * pow(error_norm, -1.0 / (double)(order + 1))) : MIN_FACTOR;
+                const double factor = (error_norm == error_norm) ? fmax(MIN_FACTOR, safety * (double)__powf((float)error_norm, -1.0f / (float)(order + 1))) : MIN_FACTOR;
                 st.h *= factor;
                 bdf_change_D<N>(B, order, factor);
                 B.n_equal = 0;
@@ -305,14 +330,14 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
         if (B.n_equal < order + 1) continue;
         // ---- order / step selection every order + 1 equal steps ----------------------------------------------------
         double f_m = 0.0, f_k, f_p = 0.0;      // candidate factors for order-1, order, order+1 (error_norm^(-1/(q+1)))
-        f_k = (error_norm > 0.0) ? pow(error_norm, -1.0 / (double)(order + 1)) : 1e300;
+        f_k = (error_norm > 1e-30) ? (double)__powf((float)error_norm, -1.0f / (float)(order + 1)) : 1e30;     // FP32 on the SFU: it only steers h
         if (order > 1) {
             double e[N];
             const double ec = kBdfKappa[order - 1] * kBdfGamma[order - 1] + 1.0 / (double)order;
 #pragma unroll
             for (int i = 0; i < N; ++i) e[i] = ec * B.D[order][i];
             const double en = bdf_rms<N>(e, scale_y, rtol, atol);
-            f_m = (en > 0.0) ? pow(en, -1.0 / (double)order) : 1e300;
+            f_m = (en > 1e-30) ? (double)__powf((float)en, -1.0f / (float)order) : 1e30;
         }
         if (order < BDF_MAX_ORDER) {
             double e[N];
@@ -320,7 +345,7 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
 #pragma unroll
             for (int i = 0; i < N; ++i) e[i] = ec * B.D[order + 2][i];
             const double en = bdf_rms<N>(e, scale_y, rtol, atol);
-            f_p = (en > 0.0) ? pow(en, -1.0 / (double)(order + 2)) : 1e300;
+            f_p = (en > 1e-30) ? (double)__powf((float)en, -1.0f / (float)(order + 2)) : 1e30;
         }
         // numpy argmax over [order-1, order, order+1]: the first maximum wins (a missing neighbour has factor 0)
         int new_order = order - 1;

@@ -15,6 +15,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __constant__ const
 #define __restrict__
 #define __shared__ static
