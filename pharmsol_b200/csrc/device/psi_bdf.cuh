@@ -194,12 +194,12 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
             B.current_jac = true;
             c_lu = 0.0;
         } else if (B.h_before_clip > st.h) {
-            // the previous call ended on a step clipped to its stop time: give the controller its step back
+            // the previous step was clipped to a stop time: give the controller its step back, at most 10x per attempt
             const double factor = fmin(MAX_FACTOR, B.h_before_clip / st.h);
             bdf_change_D<N>(B, B.order, factor);
             st.h *= factor;
             B.n_equal = 0;
-            B.h_before_clip = -1.0;
+            if (st.h >= B.h_before_clip * (1.0 - 1e-12)) B.h_before_clip = -1.0;
             c_lu = 0.0;
         }
         // ---- one step (SciPy BDF._step_impl) --------------------------------------------------------------------
@@ -212,19 +212,26 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
         int n_iter = 0;
         while (!accepted) {
             if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
-            if (st.h < 1e-14 * fmax(1.0, fabs(st.t))) return ST_SOLVER_FAILURE;
             h = st.h;
             double t_new = st.t + h;
-            if (t_new >= tstop) {
-                if (t_new > tstop) {
-                    if (B.h_before_clip <= 0.0) B.h_before_clip = st.h;
-                    bdf_change_D<N>(B, order, (tstop - st.t) / st.h);
+            const double rem = tstop - st.t;
+            // land exactly on the stop: clip, or stretch by <= 1e-9 relative so that rounding never leaves a sliver of a few
+            // ulps to be stepped separately (a sliver step used to drag the step size below the failure threshold)
+            if (h >= rem * (1.0 - 1e-9)) {
+                if (h != rem) {
+                    if (h > rem * (1.0 + 1e-9) && B.h_before_clip <= 0.0) B.h_before_clip = st.h;
+                    bdf_change_D<N>(B, order, rem / st.h);
                     B.n_equal = 0;
                     c_lu = 0.0;
                 }
                 t_new = tstop;
-                h = tstop - st.t;
+                h = rem;
                 st.h = h;
+            } else if (st.h < 2.3e-15 * fmax(1e-3, fabs(st.t))) {
+                // SciPy's min_step = 10 ulp(t): the controller (not a stop time) drove the step to nothing.  Hairer's starting
+                // step is legitimately ~1e-13 when a restart finds y ~ atol and |f| large (an infusion switching on at an
+                // emptied compartment): that must not count as a failure, the step grows 10x per accepted step from there.
+                return ST_SOLVER_FAILURE;
             }
             double ypred[N], psi[N];
 #pragma unroll
@@ -316,7 +323,7 @@ PSI_DEV int bdf_integrate_to(OdeState<N>& st, BdfState<N>& B, double tstop, F& f
         // ---- accept -----------------------------------------------------------------------------------------------------
         cnt.steps++;
         B.n_equal++;
-        st.t = (st.t + h >= tstop) ? tstop : st.t + h;
+        st.t = (h == tstop - st.t) ? tstop : st.t + h;
         B.current_jac = false;
 #pragma unroll
         for (int i = 0; i < N; ++i) {

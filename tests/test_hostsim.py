@@ -162,3 +162,17 @@ def test_sde_kernel_source_runs_single_threaded(HS, oracle):
     c = hs.run(w["support_points"], ems, seed=6, **kw)[0]
     assert np.all(np.isfinite(a)) and not np.array_equal(a, b)
     assert np.abs(a - b).max() <= 1e-3 * np.abs(a - c).max()
+
+
+def test_bdf_restart_at_an_emptied_compartment(HS):
+    """Regression: pair (subject 286, column 172) of the C4 workload.  An infusion switches on at t = 12 h when the
+    Michaelis-Menten compartment has emptied to ~atol: Hairer's starting step comes out at ~1e-13.  The BDF driver used
+    to treat that as a collapsed step (SolverFailure on the device at BASELINE size); SciPy's threshold is 10 ulp(t)."""
+    from benches import workloads as W
+    w = W.make("c4", nsub=2000, nspp=10000)
+    hs = HS(w["dsl"]).set_subjects([w["subjects"][286]])
+    spp = w["support_points"][172:173]
+    _, pred, info = hs.run(spp, None, solver="Bdf", rtol=1e-6, atol=1e-6, want_pred=True)
+    _, ref, _ = hs.run(spp, None, solver="Rodas4", rtol=1e-10, atol=1e-10, want_pred=True)
+    assert info["code"] == 0
+    assert np.max(np.abs(pred - ref) / (np.abs(ref) + 1e-2)) <= 1e-4
