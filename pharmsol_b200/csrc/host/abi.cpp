@@ -774,8 +774,14 @@ static int32_t for_each_device(pcu_ctx* ctx, F&& fn, int32_t* code, int64_t* pai
         if (r.rc != PCU_OK) r.msg = last_error();
     };
     std::vector<std::thread> workers;
-    for (int k = 1; k < n; ++k) workers.emplace_back(run, k);
+    workers.reserve((size_t)n);
+    int inline_from = n;                                  // devices whose host thread could not be started run on this one
+    for (int k = 1; k < n; ++k) {
+        try { workers.emplace_back(run, k); }
+        catch (...) { inline_from = k; break; }
+    }
     run(0);
+    for (int k = inline_from; k < n; ++k) run(k);
     for (auto& w : workers) w.join();
     cudaSetDevice(ctx->c.device);
     int32_t out_code = 0;
