@@ -295,7 +295,14 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
         __shared__ int next_particle;
         const int np = opt.nparticles;
         const int tid = threadIdx.x, B = blockDim.x;
-        double* ws = out.scratch + (long long)blockIdx.x * out.scratch_stride;
+        // particle workspace: the CTA's dynamic shared memory when it fits (1 000 particles x 1 state = 28 KB), else a slab of
+        // global scratch (L2 resident)
+#ifdef PSI_HOST_SIM
+        double* sde_smem = nullptr;
+#else
+        extern __shared__ double sde_smem[];
+#endif
+        double* ws = out.scratch_in_smem ? sde_smem : out.scratch + (long long)blockIdx.x * out.scratch_stride;
         double* bufA = ws;
         double* bufB = ws + (long long)NS * np;
         double* qv = ws + 2ll * NS * np;

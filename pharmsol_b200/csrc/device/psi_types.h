@@ -177,7 +177,7 @@ struct OutView {
     // separate collective copies afterwards.  ll is ignored then.
     double* ll_peers[8];
     int32_t npeers;
-    int32_t pad_;
+    int32_t scratch_in_smem;           // SDE: the particle workspace is the CTA's dynamic shared memory (it fits), not `scratch`
     int64_t col_base;                  // global index of local column 0 (column shards / pipelined chunks): error pair = i + (j + col_base) * nsub
 };
 
