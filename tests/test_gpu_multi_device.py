@@ -149,3 +149,22 @@ def test_few_columns_fall_back_to_the_first_device_and_uneven_shards(ps):
     assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"], ems3), ref)
     assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"][:40], ems3), ref[:, :40])      # 40 < 3 * 32
     assert np.array_equal(ps.log_likelihood_matrix(eq3, data3, w["support_points"][:1], ems3), ref[:, :1])        # latency path
+
+
+def test_long_timelines_bypass_the_shared_memory_staging(ps, oracle):
+    """A subject whose timeline program exceeds the staged window (96 records) is executed from global memory; the CTA
+    mixes both kinds of subject.  150 observations + 6 infusions vs the oracle, next to a short subject."""
+    import fixtures as FX
+    kernel = "two_compartments"
+    long_ops = [("infusion", float(6 * k), 100.0, "0", 1.5) for k in range(6)] + [("observation", 0.25 * k + 0.1, 1.0 + 0.01 * k, "0") for k in range(150)]
+    short_ops = [("bolus", 0.0, 100.0, "0"), ("observation", 1.0, 2.0, "0"), ("observation", 5.0, 1.0, "0")]
+    subjects = [("long", long_ops), ("short", short_ops), ("long2", long_ops[::-1])]
+    rng = np.random.default_rng(2)
+    spp = np.column_stack([rng.uniform(0.05, 1.0, 300), rng.uniform(0.05, 1.0, 300), rng.uniform(0.05, 1.0, 300), rng.uniform(5, 80, 300)])
+    eq = ps.Equation.from_dsl(FX.kernel_dsl(kernel))
+    data = ps.Data([ps.Subject(i, o) for i, o in subjects])
+    em = ("additive", 0.05, (0.1, 0.15, 0.0, 0.0))
+    ems = ps.AssayErrorModels().add("outeq_0", ps.AssayErrorModel.additive(ps.ErrorPoly(*em[2]), em[1]))
+    psi = ps.log_likelihood_matrix(eq, data, spp, ems)
+    ref = oracle.Model(kernel).log_likelihood_matrix(oracle.Data([oracle.Subject(o, i) for i, o in subjects]), spp, oracle.ErrorModels([em]))
+    assert np.all(np.isfinite(psi)) and np.max(np.abs(psi - ref) / (np.abs(ref) + 150)) <= 1e-12

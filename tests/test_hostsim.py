@@ -179,3 +179,15 @@ def test_bdf_restart_at_an_emptied_compartment(HS):
     _, pred9, info9 = hs.run(spp, None, solver="Bdf", rtol=1e-9, atol=1e-9, want_pred=True)
     e9 = np.max(np.abs(pred9 - ref) / (np.abs(ref) + 1e-2))
     assert info9["code"] == 0 and e6 <= 1e-3 and e9 <= 1e-5 and e9 < e6        # global error ~ 100 x tolerance on this stiff pair, and converging
+
+
+def test_program_longer_than_the_staged_window(HS, oracle):
+    """> 96 timeline-program records: the staged copy is skipped and the records are read from the global array."""
+    kernel = "two_compartments"
+    ops = [("infusion", float(6 * k), 100.0, "0", 1.5) for k in range(6)] + [("observation", 0.25 * k + 0.1, 1.0 + 0.01 * k, "0") for k in range(150)]
+    rng = np.random.default_rng(2)
+    spp = np.column_stack([rng.uniform(0.05, 1.0, 140), rng.uniform(0.05, 1.0, 140), rng.uniform(0.05, 1.0, 140), rng.uniform(5, 80, 140)])
+    em = ("additive", 0.05, (0.1, 0.15, 0.0, 0.0))
+    psi, _, info = HS(FX.kernel_dsl(kernel)).set_subjects([("long", ops), ("short", ops[:8])]).run(spp, [(1, em[1], em[2])])
+    ref = oracle.Model(kernel).log_likelihood_matrix(oracle.Data([oracle.Subject(ops, "long"), oracle.Subject(ops[:8], "short")]), spp, oracle.ErrorModels([em]))
+    assert info["code"] == 0 and np.max(np.abs(psi - ref) / (np.abs(ref) + 150)) <= 1e-12
