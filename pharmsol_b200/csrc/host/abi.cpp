@@ -577,6 +577,10 @@ int32_t pharmsol_cuda_population_set_error_models(pcu_population* pop, const pcu
         // against the contexts' non-blocking streams or a caller's stream: drain the device first so a psi kernel still
         // in flight from the asynchronous *_device / *_peers entry points never reads a half-updated timeline.
         cuda_check(cudaDeviceSynchronize(), "synchronize before re-flattening the population");
+        for (auto& r : pop->p.replicas) {      // the replicas of a multi-device context live on other devices
+            cuda_check(cudaSetDevice(r->device), "cudaSetDevice");
+            cuda_check(cudaDeviceSynchronize(), "synchronize before re-flattening the population");
+        }
         pop->p.upload();
         return (int32_t)PCU_OK;
     });
@@ -886,6 +890,11 @@ int32_t pharmsol_cuda_log_likelihood_matrix_replicated(pcu_ctx* ctx, pcu_model* 
         std::lock_guard<std::mutex> lk(ctx->c.mu);
         const int n = ctx->ndev();
         if (n > 8) throw PharmsolError(PCU_ERR_OTHER, "the replicated psi supports at most 8 devices");
+        if (gather == PCU_GATHER_PEER_STORES && !ctx->peer_enabled && n > 1) {
+            bool distinct = false;
+            for (int k = 1; k < n; ++k) distinct = distinct || ctx->dev(k).device != ctx->c.device;
+            if (distinct) throw PharmsolError(PCU_ERR_OTHER, "PCU_GATHER_PEER_STORES needs peer access between all devices of the context; use PCU_GATHER_COPY_ENGINE");
+        }
         if ((int)pop->p.replicas.size() + 1 != n) throw PharmsolError(PCU_ERR_OTHER, "population was created for another context (device list differs)");
         const int64_t nsub = pop->p.flat.nsub;
         for (int k = 0; k < n; ++k) dev_out[k] = nullptr;
