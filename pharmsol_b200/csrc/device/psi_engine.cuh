@@ -154,7 +154,7 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                     add_at<AtLeast1<NS>::v>(x, dest, amount);
                 } else {
                     if constexpr (M::OBS_USES_RATE) active_rates<NR>(inf, e.time, c.rate);
-                    c.refresh(e.time, x);
+                    if constexpr (M::OBS_NEEDS_REFRESH) c.refresh(e.time, x);
                     double y[AtLeast1<M::NOUT>::v];
 #pragma unroll
                     for (int k = 0; k < AtLeast1<M::NOUT>::v; ++k) y[k] = 0.0;
@@ -231,8 +231,8 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                 if constexpr (M::KIND == 0) st.have_k1 = false, st.h = -1.0;   // pending_reinit (ode/mod.rs:687)
             } else if (kind == EV_OBS) {
                 // observation_prediction (native.rs:1044-1086)
-                active_rates<NR>(inf, te, c.rate);
-                c.refresh(te, x);
+                if constexpr (M::OBS_USES_RATE) active_rates<NR>(inf, te, c.rate);
+                if constexpr (M::OBS_NEEDS_REFRESH) c.refresh(te, x);
                 double y[AtLeast1<M::NOUT>::v];
 #pragma unroll
                 for (int k = 0; k < AtLeast1<M::NOUT>::v; ++k) y[k] = 0.0;

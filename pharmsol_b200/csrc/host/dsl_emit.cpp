@@ -1031,6 +1031,10 @@ CompiledModel compile_model(const ModelAst& ast_in) {
     }
     // do the outputs (directly or through derive) read rate(route)?  If not, an observation needs no infusion scan
     H << "    static constexpr bool OBS_USES_RATE = " << ((((sc_out.deps | sc_derive.deps) & DEP_RATE) != 0) ? "true" : "false") << ";\n";
+    // do the outputs read covariates or derived values at all?  If not, an observation needs neither the covariate
+    // interpolation nor the derive block (the reference refreshes them unconditionally, native.rs:1044-1086; the
+    // prediction is the same)
+    H << "    static constexpr bool OBS_NEEDS_REFRESH = " << (((sc_out.deps & (DEP_DERIVED | DEP_COV)) != 0) ? "true" : "false") << ";\n";
     // pair-invariant slots: evaluated once per (subject, support point) pair right after the parameter load
     S << "    PSI_DEV static void prologue(double* p) {\n";
     for (size_t k = 0; k < em.slots.size(); ++k) S << "        p[" << (cm.parameters.size() + k) << "] = " << em.slots[k] << ";\n";
