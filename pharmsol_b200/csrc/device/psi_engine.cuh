@@ -130,7 +130,16 @@ PSI_DEV double run_pair(const PopView& pop, const RunOpts& opt, int subj, PairCt
                         for (int k = 0; k < NR; ++k) c.rate[k] = __ldg(pop.prog_rates + (long long)e.obs_row * NR + k);
                     }
                     if constexpr (!AK_HOISTED) {
-                        c.refresh(opt.cov_time == COVTIME_INTERVAL_LENGTH ? dt : e.time, x);
+                        const double tder = opt.cov_time == COVTIME_INTERVAL_LENGTH ? dt : e.time;
+                        bool done = false;
+                        if constexpr (M::NCOV == 1 && NR == 1 && M::HAS_DERIVE) {
+                            if (pop.prog_cov) {       // the host has interpolated the covariate for both derive-time conventions
+                                c.cov[0] = opt.cov_time == COVTIME_INTERVAL_LENGTH ? e.sigma : e.w;
+                                M::derive(tder, x, c.p, c.cov, c.rate, c.d);
+                                done = true;
+                            }
+                        }
+                        if (!done) c.refresh(tder, x);
                         double kp[8];
                         M::kparams(c.p, c.d, kp);
                         ak.setup_kp(kp, status);

@@ -69,7 +69,9 @@ struct __attribute__((aligned(16))) EventRec {
 //   EV_BOLUS / EV_OBS   the event record unchanged (infusion events carry no action and are dropped)
 //   EV_STEP             time = sub-interval end, a = dt (the same IEEE difference the device formed per pair),
 //                       b / w / sigma = rate of route 0 / 1 / 2 on the sub-interval; with more than 3 routes obs_row
-//                       indexes PopView::prog_rates (route_len doubles per step)
+//                       indexes PopView::prog_rates (route_len doubles per step).  One route and one covariate
+//                       (PopView::prog_cov): w / sigma = the covariate interpolated at the sub-interval end / at t = dt
+//                       (the two derive-time conventions, COVTIME_*), so the step needs no segment scan
 // so a pair costs one broadcast load + arithmetic per record: no cursor, no boundary scan, no infusion scan.
 __host__ __device__ inline int ev_kind(int meta) { return meta & 3; }
 __host__ __device__ inline int ev_cens(int meta) { return (meta >> 2) & 3; }
@@ -115,7 +117,8 @@ struct PopView {
     int32_t nsub;
     int32_t ncov;
     int32_t max_events;           // max events in any occasion
-    int32_t pad;
+    int32_t prog_cov;             // 1: models with ONE covariate and one route carry the interpolated covariate in the EV_STEP
+                                  //    records (w = value at the sub-interval end, sigma = value at t = dt), see data.cpp
 };
 
 // 0-4 are this backend's own integrators; 5-6 carry the reference's remaining solver names (ode/mod.rs:59-84):

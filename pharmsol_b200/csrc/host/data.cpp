@@ -171,10 +171,11 @@ FlatPopulation flatten_population(const Data& data, const ModelLabels& labels, c
     f.has_prog = true;
     for (const auto& r : labels.routes) if (r.has_lag) f.has_prog = false;      // lagged bolus times depend on the support point
     const int nroute = std::max(1, labels.route_len);
+    f.prog_cov = f.has_prog && nroute == 1 && labels.covariates.size() == 1;
     f.prog_offsets.push_back(0);
     for (const auto& subj : data.subjects) {
         for (const auto& occ : subj.occasions) {
-            const size_t ev_first = f.events.size(), inf_first = f.infs.size();
+            const size_t ev_first = f.events.size(), inf_first = f.infs.size(), prog_first = f.prog.size(), seg_first = f.cov_segs.size();
             f.occ_index.push_back(occ.index);
             f.occ_t0.push_back(occ.initial_time());
             std::vector<double> bounds;
@@ -293,6 +294,22 @@ FlatPopulation flatten_population(const Data& data, const ModelLabels& labels, c
                     }
                 }
                 f.cov_offsets.push_back((int32_t)f.cov_segs.size());
+            }
+            if (f.has_prog && f.prog_cov) {
+                // Covariate::interpolate (covariate.rs:216-241) on the segments just built: first segment with from <= t < to
+                auto cov_at = [&](double t) {
+                    for (size_t q = seg_first; q < f.cov_segs.size(); ++q) {
+                        const CovSeg& sg = f.cov_segs[q];
+                        if (sg.from <= t && t < sg.to) return sg.slope * t + sg.intercept;
+                    }
+                    return std::numeric_limits<double>::quiet_NaN();
+                };
+                for (size_t q = prog_first; q < f.prog.size(); ++q) {
+                    EventRec& r = f.prog[q];
+                    if (ev_kind(r.meta) != EV_STEP) continue;
+                    r.w = cov_at(r.time);       // COVTIME_INTERVAL_END
+                    r.sigma = cov_at(r.a);      // COVTIME_INTERVAL_LENGTH (analytical! macro quirk: derive at t = dt)
+                }
             }
             f.ev_offsets.push_back((int32_t)f.events.size());
             f.bol_offsets.push_back((int32_t)f.bol_event.size());

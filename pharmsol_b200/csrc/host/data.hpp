@@ -139,6 +139,7 @@ struct FlatPopulation {
     std::vector<psi::EventRec> prog;
     std::vector<double> prog_rates;
     bool has_prog = false;
+    bool prog_cov = false;              // EV_STEP records carry the single covariate's value (w: at the end, sigma: at t = dt)
     int32_t nsub = 0, ncov = 0, max_events = 0;
     int64_t nobs_total = 0;
     bool has_lagged_candidates = false;

@@ -111,6 +111,7 @@ int hs_run(void* p, int solver, const double* spp_rows, long nspp, int np, const
         v.occ_t0 = f.occ_t0.data(); v.nsub = f.nsub; v.ncov = f.ncov; v.max_events = f.max_events;
         v.prog_offsets = f.has_prog ? f.prog_offsets.data() : nullptr; v.prog = f.has_prog ? f.prog.data() : nullptr;
         v.prog_rates = f.has_prog ? f.prog_rates.data() : nullptr;
+        v.prog_cov = f.prog_cov ? 1 : 0;
         std::vector<double> soa((size_t)np * nspp);
         for (long j = 0; j < nspp; ++j)
             for (int k = 0; k < np; ++k) soa[(size_t)k * nspp + j] = spp_rows[(size_t)j * np + k];
