@@ -17,6 +17,31 @@ namespace psi {
 PSI_DEV double psi_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 PSI_DEV double psi_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
+// reciprocal to ~2^-20 with ONE MUFU.RCP64H and no Newton refinement: enough for the weights of an
+// error norm, and it moves the work from the FP64 pipe (the bound of these kernels) to the XU pipe.
+PSI_DEV double rcp_approx(double x) {
+#ifdef PSI_HOST_SIM      // tests/hostsim: the device headers compiled for the host (test infrastructure)
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#endif
+}
+
+// Reciprocal / quotient to ~1 ulp without the IEEE fix-up path: MUFU.RCP64H seed + two Newton steps (4 DFMA).  CUDA's
+// `a / b` costs ~14 instructions plus a divergence-scoped branch to a slow path (ncu on the RODAS4 kernel: FSEL + FSETP +
+// BSSY / BSYNC / BRA are 25 % of the executed instructions, most of them the fix-ups of ~10 divisions per step).  Used
+// where the last bit does not matter: the emitted ODE dynamics / Jacobian (the solver's tolerance dominates), the LU
+// pivots and 1/h.  Zero, infinite or denormal divisors give inf / 0 / inf like the seed does (ftz); NaN propagates.
+PSI_DEV double rcp_nr(double x) {
+    double r = rcp_approx(x);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+PSI_DEV double fdiv(double a, double b) { return a * rcp_nr(b); }
+
 // ---------------------------------------------------------------------------------------------
 // Covariates.  The host flattener emits, per (occasion, covariate), a leading sentinel segment
 // (-inf, first.from) carrying the first observation's value, then the reference's segments with

@@ -15,18 +15,6 @@
 
 namespace psi {
 
-// reciprocal to ~2^-20 with ONE MUFU.RCP64H and no Newton refinement: enough for the weights of an
-// error norm, and it moves the work from the FP64 pipe (the bound of these kernels) to the XU pipe.
-PSI_DEV double rcp_approx(double x) {
-#ifdef PSI_HOST_SIM      // tests/hostsim: the device headers compiled for the host (test infrastructure)
-    return 1.0 / x;
-#else
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-#endif
-}
-
 // The tableau coefficients live in the constant bank so DFMA reads them as c[3][..] operands; as
 // constexpr literals the compiler re-materialises each 64-bit immediate with two UMOVs per use
 // (88 UMOV per Dopri5 step in the first build).  The constexpr copies stay for compile-time zero tests.

@@ -47,7 +47,7 @@ struct SmallLU {
             }
             const double piv = a[k * N + k];
             if (piv == 0.0 || piv != piv) singular = true;
-            const double ip = 1.0 / piv;
+            const double ip = rcp_nr(piv);      // ~1 ulp, no IEEE fix-up path (psi_common.cuh)
             a[k * N + k] = ip;                 // store the reciprocal pivot
 #pragma unroll
             for (int i = k + 1; i < N; ++i) {
@@ -335,7 +335,7 @@ PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
         const double rem = tstop - st.t;
         const bool last = st.h >= rem;
         const double h = last ? rem : st.h;
-        const double ih = 1.0 / h;
+        const double ih = rcp_nr(h);
         const double ihg = ih * (1.0 / g);
         // E = I/(h g) - J, factored in registers (J is re-evaluated instead of stored: a Jacobian costs
         // about one RHS, N*N registers cost occupancy)

@@ -334,7 +334,10 @@ struct Emitter {
             Val x = real(a), y = real(b);
             if (x.is_const && y.is_const) return mkconst(x.cval / y.cval, Ty::Real);
             const std::string rc = reciprocal(e->args[1], y, s);
-            Val r; r.code = rc.empty() ? "(" + x.code + " / " + y.code + ")" : "(" + x.code + " * " + rc + ")"; return r;
+            // ODE / SDE dynamics and the Jacobian pass: ~1-ulp quotient without the IEEE fix-up path (psi::fdiv); everything a
+            // prediction or likelihood is computed from directly (derive, outputs, init, lag, fa) keeps the exact division
+            const bool fast = s.ad || s.role == Role::Dynamics || s.role == Role::Diffusion;
+            Val r; r.code = !rc.empty() ? "(" + x.code + " * " + rc + ")" : fast ? "psi::fdiv(" + x.code + ", " + y.code + ")" : "(" + x.code + " / " + y.code + ")"; return r;
         }
         if (op == "^") {
             Val x = real(a), y = real(b);
@@ -444,8 +447,8 @@ struct Emitter {
                 if (op == "/") {
                     // (a/b)' = a'/b - a b'/b^2
                     const std::string rc = reciprocal(e->args[1], b, s);
-                    std::string t1 = da.empty() ? "" : rc.empty() ? "(" + da + " / " + b.code + ")" : "(" + da + " * " + rc + ")";
-                    std::string t2 = db.empty() ? "" : "((" + a.code + " * " + db + ") / (" + b.code + " * " + b.code + "))";
+                    std::string t1 = da.empty() ? "" : rc.empty() ? "psi::fdiv(" + da + ", " + b.code + ")" : "(" + da + " * " + rc + ")";
+                    std::string t2 = db.empty() ? "" : "psi::fdiv((" + a.code + " * " + db + "), (" + b.code + " * " + b.code + "))";
                     return t2.empty() ? t1 : t1.empty() ? "(-" + t2 + ")" : "(" + t1 + " - " + t2 + ")";
                 }
                 if (op == "^") return deriv_pow(a, b, da, db);
@@ -1105,6 +1108,7 @@ std::string CompiledModel::host_source() const {
          "inline double pow_2(double x) { return x * x; }\n"
          "inline double pow_3(double x) { return (x * x) * x; }\n"
          "inline double pow_4(double x) { const double q = x * x; return q * q; }\n"
+         "inline double fdiv(double a, double b) { return a / b; }\n"
          "}  // namespace psi\n";
     o << "namespace {\nstruct Model {\n" << body << "};\n";
     o << "inline void load_params(const double* params, double* p) {\n    for (int k = 0; k < Model::NP; ++k) p[k] = params[k];\n    Model::prologue(p);\n}\n";
