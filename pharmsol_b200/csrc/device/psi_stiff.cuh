@@ -81,6 +81,30 @@ struct SmallLU {
     }
 };
 
+// N = 2 (the effect-compartment PD models of the C4 kind): the explicit inverse by the adjugate instead of pivoted
+// elimination.  The conditional row swaps of the generic LU are 64-bit selects in `factor` and in every one of the six
+// `solve` calls of a RODAS4 step — ncu on C4: FSEL was 12 % of the executed instructions — while a 2 x 2 inverse is one
+// determinant (an FMA pair), one reciprocal and four products, and a solve is two FMA pairs with no data-dependent
+// permutation.  E = I/(h gamma) - J is diagonally dominated by 1/(h gamma) for the steps the controller accepts; a
+// vanishing or non-finite determinant is reported as singular exactly like a zero pivot.
+template <>
+struct SmallLU<2> {
+    double a[4];          // in: the matrix (row-major); after factor(): its inverse
+    bool singular;
+    PSI_DEV void factor() {
+        const double det = fma(a[0], a[3], -(a[1] * a[2]));
+        singular = (det == 0.0) || (det != det);
+        const double id = rcp_nr(det);
+        const double i00 = a[3] * id, i01 = -a[1] * id, i10 = -a[2] * id, i11 = a[0] * id;
+        a[0] = i00; a[1] = i01; a[2] = i10; a[3] = i11;
+    }
+    PSI_DEV void solve(double* b) const {
+        const double b0 = b[0], b1 = b[1];
+        b[0] = fma(a[0], b0, a[1] * b1);
+        b[1] = fma(a[2], b0, a[3] * b1);
+    }
+};
+
 struct Sdirk4Tab {
     static constexpr int S = 5;
     static constexpr int EST_ORDER = 3;
