@@ -72,53 +72,13 @@ PSI_DEV void fill_cov(const PopView& pop, int occ, double t, double* cov) {
     }
 }
 
-// sqrt(x) for finite x > 0 to <= 1 ulp without the library's fix-up path: MUFU.RSQ64H seed, two Newton steps on the reciprocal
-// root, one Heron correction with the exact residual (11 instructions; CUDA's sqrt costs ~35 with its slow-path
-// scaffolding — ncu attributes 6 % of the 3-compartment kernel's instructions to four square roots per step).  Zero,
-// negative, infinite or NaN arguments take the library call.
-PSI_DEV double sqrt_nr(double x) {
-#ifdef PSI_HOST_SIM
-    return sqrt(x);
-#else
-    if (!(x > 0.0) || !(x < 1e300)) return sqrt(x);
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-    r = fma(r, fma(-hx * r, r, 0.5), r);      // r <- r (1.5 - 0.5 x r^2)
-    r = fma(r, fma(-hx * r, r, 0.5), r);
-    double s = x * r;
-    s = fma(fma(-s, s, x), 0.5 * r, s);      // s <- s + (x - s^2) / (2 s)
-    return s;
-#endif
-}
-
-// sin and cos of a SMALL angle (|x| <= 1.1; the trisected angle of the three-compartment cubic lives in [0, pi/3]): the
-// Taylor polynomials to x^17 / x^18 (truncation < 3e-17 relative at pi/3) in Horner form with the coefficients in the
-// constant bank — no range reduction, no Payne-Hanek test (22 instructions against ~70 for sincos()).  Larger arguments
-// take the library call.
-static __constant__ double kSinC[9] = {1.0, -0.16666666666666666, 0.008333333333333333, -0.0001984126984126984, 2.7557319223985893e-06,
-                                       -2.505210838544172e-08, 1.6059043836821613e-10, -7.647163731819816e-13, 2.8114572543455206e-15};
-static __constant__ double kCosC[10] = {1.0, -0.5, 0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05, -2.755731922398589e-07,
-                                        2.08767569878681e-09, -1.1470745597729725e-11, 4.779477332387385e-14, -1.5619206968586225e-16};
-PSI_DEV void sincos_small(double x, double* sn, double* cs) {
-    if (!(fabs(x) <= 1.1)) { sincos(x, sn, cs); return; }
-    const double z = x * x;
-    double ps = kSinC[8], pc = kCosC[9];
-#pragma unroll
-    for (int k = 7; k >= 0; --k) ps = fma(ps, z, kSinC[k]);
-#pragma unroll
-    for (int k = 8; k >= 0; --k) pc = fma(pc, z, kCosC[k]);
-    *sn = x * ps;
-    *cs = pc;
-}
-
 // pow(x, c) for the exponents PK models actually use (allometric 0.75 / 0.25, square roots, small integers): square
 // roots and multiplications instead of the ~150-instruction general pow.  sqrt is correctly rounded, so these are
 // within 1.5 ulp — the same class as CUDA's pow (2 ulp) and the reference's libm powf.
-PSI_DEV double pow_half(double x) { return sqrt_nr(x); }
-PSI_DEV double pow_quarter(double x) { return sqrt_nr(sqrt_nr(x)); }
-PSI_DEV double pow_three_quarters(double x) { const double s = sqrt_nr(x); return s * sqrt_nr(s); }
-PSI_DEV double pow_three_halves(double x) { return x * sqrt_nr(x); }
+PSI_DEV double pow_half(double x) { return sqrt(x); }
+PSI_DEV double pow_quarter(double x) { return sqrt(sqrt(x)); }
+PSI_DEV double pow_three_quarters(double x) { const double s = sqrt(x); return s * sqrt(s); }
+PSI_DEV double pow_three_halves(double x) { return x * sqrt(x); }
 PSI_DEV double pow_2(double x) { return x * x; }
 PSI_DEV double pow_3(double x) { return (x * x) * x; }
 PSI_DEV double pow_4(double x) { const double q = x * x; return q * q; }
