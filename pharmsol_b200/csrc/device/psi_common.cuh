@@ -29,6 +29,28 @@ PSI_DEV double rcp_approx(double x) {
 #endif
 }
 
+// x^p for the step-size controllers, x > 0 a normal float: MUFU.LG2 * p -> MUFU.EX2 with flush-to-zero and none of __powf's
+// denormal scaling (ncu: the controller's __powf was 5 % of the Dopri5 kernel's instructions; it only steers h).
+PSI_DEV float powf_fast(float x, float p) {
+#ifdef PSI_HOST_SIM
+    return __powf(x, p);
+#else
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    l *= p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return r;
+#endif
+}
+
+// max(|a|, |b|) of two finite doubles on the INTEGER pipe: non-negative doubles order like their bit patterns.  The error
+// norms of the explicit pairs need it once per component per step, and DSETP / FP64 selects would add to the pipe that
+// bounds those kernels.  A NaN input gives a NaN-or-larger pattern; the step is then rejected by the non-finite error test.
+PSI_DEV double max_abs(double a, double b) {
+    const long long ia = __double_as_longlong(a) & 0x7fffffffffffffffLL, ib = __double_as_longlong(b) & 0x7fffffffffffffffLL;
+    return __longlong_as_double(ia > ib ? ia : ib);
+}
+
 // Reciprocal / quotient to ~1 ulp without the IEEE fix-up path: MUFU.RCP64H seed + two Newton steps (4 DFMA).  CUDA's
 // `a / b` costs ~14 instructions plus a divergence-scoped branch to a slow path (ncu on the RODAS4 kernel: FSEL + FSETP +
 // BSSY / BSYNC / BRA are 25 % of the executed instructions, most of them the fix-ups of ~10 divisions per step).  Used

@@ -174,7 +174,7 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
 #pragma unroll
             for (int j = 0; j < TAB::S; ++j)
                 if (TAB::e(j) != 0.0) e = fma(TAB::ce(j), k[j][i], e);
-            const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
+            const double sc = fma(rtol, max_abs(st.y[i], ynew[i]), atol);
             const double q = (h * e) * rcp_approx(sc);
             err2 = fma(q, q, err2);
         }
@@ -187,7 +187,7 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
         }
         // fac = 0.9 * err^(-1/5), err = sqrt(err2 / N)  =>  0.9 * (err2 / N)^(-1/10)
         const float e2 = (float)err2 * (1.0f / N);
-        float fac = (e2 <= 1e-30f) ? 10.0f : 0.9f * __powf(e2, -0.1f);
+        float fac = (e2 <= 1e-30f) ? 10.0f : 0.9f * powf_fast(e2, -0.1f);
         fac = fminf(10.0f, fmaxf(0.2f, fac));
         if (err2 <= (double)N) {
             cnt.steps++;

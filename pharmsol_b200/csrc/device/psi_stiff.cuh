@@ -415,7 +415,7 @@ PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             ynew[i] = u[i] + K[5][i];
-            const double sc = fma(rtol, fmax(fabs(st.y[i]), fabs(ynew[i])), atol);
+            const double sc = fma(rtol, max_abs(st.y[i], ynew[i]), atol);
             const double q = K[5][i] * rcp_approx(sc);
             err2 = fma(q, q, err2);
         }
@@ -427,7 +427,7 @@ PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
         }
         // fac = 0.9 * err^(-1/4), err = sqrt(err2 / N)
         const float e2 = (float)err2 * (1.0f / N);
-        float fac = (e2 <= 1e-30f) ? 6.0f : 0.9f * __powf(e2, -0.125f);
+        float fac = (e2 <= 1e-30f) ? 6.0f : 0.9f * powf_fast(e2, -0.125f);
         fac = fminf(6.0f, fmaxf(0.2f, fac));
         if (err2 <= (double)N) {
             cnt.steps++;
