@@ -51,6 +51,34 @@ PSI_DEV double max_abs(double a, double b) {
     return __longlong_as_double(ia > ib ? ia : ib);
 }
 
+// min / max of two doubles of which at most one is negative (and neither is -0), on the integer pipe: such doubles order
+// like their bit patterns read as signed 64-bit integers.  +NaN orders above +inf.
+PSI_DEV double max_pos(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
+PSI_DEV double min_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b) ? a : b; }
+
+// Single-MUFU FP32 helpers without the denormal fix-ups of __logf / sqrtf / rsqrtf (arguments are normal or +-0 / inf)
+PSI_DEV float lg2_ftz(float x) {
+#ifdef PSI_HOST_SIM
+    return log2f(x);
+#else
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+PSI_DEV float sqrt_ftz(float x) {
+#ifdef PSI_HOST_SIM
+    return sqrtf(x);
+#else
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+PSI_DEV float rsqrt_ftz(float x) {
+#ifdef PSI_HOST_SIM
+    return 1.0f / sqrtf(x);
+#else
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+
 // Reciprocal / quotient to ~1 ulp without the IEEE fix-up path: MUFU.RCP64H seed + two Newton steps (4 DFMA).  CUDA's
 // `a / b` costs ~14 instructions plus a divergence-scoped branch to a slow path (ncu on the RODAS4 kernel: FSEL + FSETP +
 // BSSY / BSYNC / BRA are 25 % of the executed instructions, most of them the fix-ups of ~10 divisions per step).  Used

@@ -42,8 +42,8 @@ struct Philox {
 
 // Per-particle normal stream: one Philox block = 4 normals.  Everything is indexed statically so the normals stay in
 // registers (a runtime-indexed buffer would live in local memory).
-// Precision of the noise (RunOpts::sde_normals): the default draws Box-Muller normals in FP32 from 24-bit uniforms on the
-// SFU (MUFU.LG2 / SIN / COS): |z| <= 5.77, resolution 2^-24 near 0 — narrower than the f64 `Normal` the reference samples
+// Precision of the noise (RunOpts::sde_normals): the default draws Box-Muller normals in FP32 (32-bit Philox words rounded
+// to FP32 uniforms) on the SFU (MUFU.LG2 / SQRT / SIN / COS): |z| <= 6.76, 24-bit mantissa — narrower than the f64 `Normal` the reference samples
 // (sde/em.rs:104-120), chosen because the stepper is bound by integer / SFU issue and an FP64 Box-Muller triples the cost
 // of a draw.  SDE_NORMALS_FP64 evaluates the same transform in FP64 from 32-bit uniforms (|z| <= 6.66); the particle-filter
 // likelihood does not distinguish the two (tests/test_gpu_sde_parity.py compares them at equal seed counts).
@@ -73,11 +73,12 @@ struct NormalStream {
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float u1 = ((float)(r[2 * i] >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
-            const float u2 = ((float)(r[2 * i + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float rad = sqrtf(-2.0f * __logf(u1));
+            // a 32-bit word rounded to FP32: u1 in [2^-33, 1], the angle in (0, 2 pi]; -2 ln u = -2 ln 2 * lg2 u
+            const float u1 = fmaf((float)r[2 * i], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            const float a2 = fmaf((float)r[2 * i + 1], 1.4629180792671596e-09f, 7.314590396335798e-10f);
+            const float rad = sqrt_ftz(-1.3862943611198906f * lg2_ftz(u1));
             float sn, cs;
-            __sincosf(6.2831853071795865f * u2, &sn, &cs);
+            __sincosf(a2, &sn, &cs);
             z[2 * i] = (double)(rad * cs);
             z[2 * i + 1] = (double)(rad * sn);
         }
@@ -122,8 +123,28 @@ PSI_DEV double sqrt_fast(double x) {
 #endif
     const double hx = 0.5 * x;
     r = fma(r, fma(-hx * r, r, 0.5), r);       // r <- r (1.5 - 0.5 x r^2)
-    r = fma(r, fma(-hx * r, r, 0.5), r);
     return x * r;
+}
+
+// drift rule of the reference: every infusion with start <= t <= start + duration (sde/mod.rs:124-133); `until` is the
+// first start / end after t, up to which the set cannot change
+template <int NR>
+struct RateWindow { double rate[NR]; double until; };
+template <int NR>
+__device__ __noinline__ RateWindow<NR> sde_rate_window(const InfRec* p, int n, double t) {
+    RateWindow<NR> w;
+    w.until = psi_inf();
+#pragma unroll
+    for (int k = 0; k < NR; ++k) w.rate[k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double s, d, a; int input;
+        load_inf(p + i, s, d, a, input);
+        const double e = s + d;
+        if (t >= s && t <= e) add_rate<NR>(w.rate, input, a);
+        if (s > t) w.until = fmin(w.until, s);
+        if (e >= t) w.until = fmin(w.until, e);
+    }
+    return w;
 }
 
 template <class M>
@@ -136,22 +157,15 @@ struct SdeStep {
     double rate_from, rate_until;
     PSI_DEV SdeStep(PairCtx<M>& cc, InfRange r) : c(cc), inf(r), rate_from(1.0), rate_until(0.0) {}
     PSI_DEV void invalidate_rates() { rate_from = 1.0; rate_until = 0.0; }
-    // drift rule of the reference: every infusion with start <= t <= start + duration (sde/mod.rs:124-133)
+    // The window test is all the hot loop sees (1 % of the evaluations on C5 leave it); the recomputation is an out-of-line
+    // call so that the compiler cannot fold its first statements into selects executed by every evaluation.
     PSI_DEV void rates_at(double t) {
         if (t >= rate_from && t < rate_until) return;
-        double until = psi_inf();
+        const RateWindow<NR> w = sde_rate_window<NR>(inf.p, inf.n, t);
 #pragma unroll
-        for (int k = 0; k < NR; ++k) c.rate[k] = 0.0;
-        for (int i = 0; i < inf.n; ++i) {
-            double s, d, a; int input;
-            load_inf(inf.p + i, s, d, a, input);
-            const double e = s + d;
-            if (t >= s && t <= e) add_rate<NR>(c.rate, input, a);
-            if (s > t) until = fmin(until, s);
-            if (e >= t) until = fmin(until, e);
-        }
+        for (int k = 0; k < NR; ++k) c.rate[k] = w.rate[k];
         rate_from = t;
-        rate_until = until;       // at t == until the set is recomputed (closed interval ends)
+        rate_until = w.until;     // at t == until the set is recomputed (closed interval ends)
     }
     // drift + diffusion at (t, x): derive/covariates refreshed at absolute t (native.rs:2330-2420)
     PSI_DEV void eval(double t, const double* x, double* dx, double* g) {
@@ -182,48 +196,78 @@ struct SdeStep {
             y2[k] = fma(dx[k], hdt, fma(g[k] * z[NS + k], sqh, x[k]));
         }
     }
-    // em.rs:134-167
-    PSI_DEV void solve_reference(double t0, double tf, double* x, NormalStream& rng, Counters& cnt) {
-        double t = t0, dt = 0.1;
-        int guard = 0;
-        while (t < tf) {
-            if (++guard > 4000000) break;
-            double y1[NS], y2[NS];
-            double z[4 * ((3 * NS + 3) / 4)];
-            rng.template fill<3 * NS>(z);                     // three INDEPENDENT draws per state (em.rs:104-120)
-            const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
-            em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
-            em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
-            cnt.evals += 3;                                  // algorithmic count (the reference evaluates the pair three times)
-            // err only steers dt: the weight 1/tol uses the one-MUFU reciprocal and the new step the FP32 rsqrt
-            double err = 0.0;
+    // Normal bookkeeping of the reference stepper.  One attempt consumes NEED = 3*NSTATE normals (three INDEPENDENT draws
+    // per state, em.rs:104-120) and a Philox block yields 4, so a particle's attempts run in a cycle of PERIOD attempts
+    // over which whole blocks are used up exactly; within the cycle the leftover normals of a block are carried into the
+    // next attempt (NSTATE = 1: 4 attempts per 3 blocks instead of 4 — a quarter of the generator work, which is what
+    // bounds this kernel).  All indices below are compile-time, so the carry stays in registers.
+    static constexpr int NEED = 3 * NS;
+    static constexpr int PERIOD = (NEED % 4 == 0) ? 1 : ((NEED % 2 == 0) ? 2 : 4);
+    // em.rs:134-167, one attempt of one particle at cycle position PHASE
+    template <int PHASE>
+    PSI_DEV void attempt(double tf, double* x, double& t, double& dt, NormalStream& rng, double* carry, Counters& cnt) {
+        constexpr int L = 4 * ((NEED * PHASE + 3) / 4) - NEED * PHASE;   // normals left over by the attempts before this one
+        constexpr int NB = (NEED - L + 3) / 4, L2 = L + 4 * NB - NEED;    // blocks to draw now, normals left over after
+        double z[L + 4 * NB + 1];
 #pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                const double tol = fma(1e-2, fabs(x[k]), 1e-2);
-                err = fmax(err, fabs(y1[k] - y2[k]) * rcp_approx(tol));
-            }
-            double nd = dt * (double)(0.9f * rsqrtf((float)err));
-            nd = fmin(fmax(nd, 1e-6), 0.1);
-            if (err <= 1.0) {
-                cnt.steps++;
-                t += dt;
+        for (int i = 0; i < L; ++i) z[i] = carry[i];
 #pragma unroll
-                for (int k = 0; k < NS; ++k) x[k] = y2[k];
-                dt = fmin(nd, tf - t);
-            } else {
-                cnt.rejected++;
-                dt = nd;
+        for (int b = 0; b < NB; ++b) rng.block4(z + L + 4 * b);
+#pragma unroll
+        for (int i = 0; i < L2; ++i) carry[i] = z[NEED + i];
+        double y1[NS], y2[NS];
+        const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
+        em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
+        em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
+        cnt.evals += 3;                                  // algorithmic count (the reference evaluates the pair three times)
+        // err only steers dt: the weight 1/tol uses the one-MUFU reciprocal and the new step the FP32 rsqrt; err, nd and
+        // tf - t are compared on the integer pipe (err >= 0, nd >= 0; tf - t < 0 only on the overshooting first attempt)
+        double err = fabs(y1[0] - y2[0]) * rcp_approx(fma(1e-2, fabs(x[0]), 1e-2));
+#pragma unroll
+        for (int q = 1; q < NS; ++q) {
+            const double tol = fma(1e-2, fabs(x[q]), 1e-2);
+            err = max_pos(err, fabs(y1[q] - y2[q]) * rcp_approx(tol));
+        }
+        double nd = dt * (double)(0.9f * rsqrt_ftz((float)err));
+        nd = min_pos(max_pos(nd, 1e-6), 0.1);
+        if (err <= 1.0) {
+            cnt.steps++;
+            t += dt;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) x[q] = y2[q];
+            dt = min_pos(nd, tf - t);
+        } else {
+            cnt.rejected++;
+            dt = nd;
+        }
+    }
+    template <int PHASE>
+    PSI_DEV void cycle(double tf, double* x, double& t, double& dt, int& guard, bool& active, int k, double* buf, int np,
+                       NormalStream& rng, double* carry, Counters& cnt) {
+        if constexpr (PHASE < PERIOD) {
+            if (active) {
+                attempt<PHASE>(tf, x, t, dt, rng, carry, cnt);
+                if (!(t < tf) || ++guard > 4000000) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) buf[(long long)s * np + k] = x[s];
+                    active = false;
+                }
             }
+            cycle<PHASE + 1>(tf, x, t, dt, guard, active, k, buf, np, rng, carry, cnt);
         }
     }
     // The reference stepper over ALL particles of the CTA with lane-level dynamic scheduling: the number of
     // attempts per particle is random (the error estimate is noise-dominated), so a static particle->lane
     // map leaves a quarter of the lanes idle (ncu: 24.0 active threads per instruction).  Here every lane
-    // runs one flat "one attempt" loop and fetches the next particle from a CTA-wide counter the moment its
-    // own finishes.  Results do not depend on the schedule: the Philox stream is keyed by the particle.
+    // runs cycles of PERIOD attempts and fetches the next particle from a CTA-wide counter at the first cycle
+    // boundary after its own finishes — every lane of a warp is then at the same cycle position, so the block
+    // generation of a position is skipped by the whole warp where the carry covers it; a particle that ends
+    // mid-cycle idles its lane for at most PERIOD-1 attempts out of the hundreds an interval takes.  Results do
+    // not depend on the schedule: the Philox stream, and the position in it, are functions of the particle alone.
     PSI_DEV void solve_reference_all(double t0, double tf, double* buf, int np, int* next, NormalStream& rng,
                                      unsigned int seq, unsigned int pair, Counters& cnt) {
         double x[NS];
+        double carry[4];
         double t = t0, dt = 0.1;
         int k = -1, guard = 0;
         bool active = false;
@@ -236,36 +280,7 @@ struct SdeStep {
                 rng.reset((unsigned int)k, seq, pair);
                 t = t0; dt = 0.1; guard = 0; active = true;
             }
-            double y1[NS], y2[NS];
-            double z[4 * ((3 * NS + 3) / 4)];
-            rng.template fill<3 * NS>(z);
-            const double sq = sqrt_fast(dt), sqh = sq * 0.70710678118654752;
-            em_first(t, dt, sq, sqh, x, y1, y2, z);          // full step and first half step share drift / diffusion at (t, x)
-            em_step(fma(dt, 0.5, t), dt * 0.5, sqh, y2, z + 2 * NS);
-            cnt.evals += 3;                                  // algorithmic count (the reference evaluates the pair three times)
-            double err = 0.0;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) {
-                const double tol = fma(1e-2, fabs(x[q]), 1e-2);
-                err = fmax(err, fabs(y1[q] - y2[q]) * rcp_approx(tol));
-            }
-            double nd = dt * (double)(0.9f * rsqrtf((float)err));
-            nd = fmin(fmax(nd, 1e-6), 0.1);
-            if (err <= 1.0) {
-                cnt.steps++;
-                t += dt;
-#pragma unroll
-                for (int q = 0; q < NS; ++q) x[q] = y2[q];
-                dt = fmin(nd, tf - t);
-            } else {
-                cnt.rejected++;
-                dt = nd;
-            }
-            if (!(t < tf) || ++guard > 4000000) {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) buf[(long long)s * np + k] = x[s];
-                active = false;
-            }
+            cycle<0>(tf, x, t, dt, guard, active, k, buf, np, rng, carry, cnt);
         }
     }
     PSI_DEV void solve_fixed(double t0, double tf, double hmax, double* x, NormalStream& rng, Counters& cnt) {
