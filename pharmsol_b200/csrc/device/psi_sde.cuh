@@ -299,7 +299,8 @@ struct SdeStep {
     }
 };
 
-// Workspace per CTA (global memory, L2 resident): 2 state buffers [NSTATE][np], q[np], anc[np]
+// Workspace per CTA (shared memory when it fits, else global scratch): 2 state buffers [NSTATE][np] that swap roles at
+// every resampling, the weights in the first np slots of the idle one, and anc[np] (launch_geometry.hpp)
 template <class M>
 __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const double* __restrict__ spp, long long ncols,
                                                     long long spp_ld, const RunOpts& opt, const OutView& out) {
@@ -320,14 +321,18 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
         double* ws = out.scratch_in_smem ? sde_smem : out.scratch + (long long)blockIdx.x * out.scratch_stride;
         double* bufA = ws;
         double* bufB = ws + (long long)NS * np;
-        double* qv = ws + 2ll * NS * np;
-        int* anc = reinterpret_cast<int*>(ws + 2ll * NS * np + np);
+        int* anc = reinterpret_cast<int*>(ws + 2ll * NS * np);
         Counters cnt;
         // log_likelihood_batch (likelihood/mod.rs:119-177): CTA q evaluates subject q with parameter row q; the score is the
         // residual-error likelihood of the particle-MEAN predictions (estimate_predictions of an SDE, sde/mod.rs:387-433)
         const bool diag = opt.diagonal != 0;
         const long long npairs = diag ? (ncols < pop.nsub ? ncols : (long long)pop.nsub) : (long long)pop.nsub * ncols;
-        for (long long lpair = blockIdx.x; lpair < npairs; lpair += gridDim.x) {
+        // Pairs differ in cost (the adaptive stepper's attempt count depends on the parameters): after its first pair a CTA
+        // draws the next one from a launch-wide ticket instead of striding, so no CTA ends long after the others.  psi does
+        // not depend on the assignment (streams are keyed by the global pair).
+        __shared__ long long next_pair;
+        long long lpair = blockIdx.x;
+        while (lpair < npairs) {
             const int subj = diag ? (int)lpair : (int)(lpair % pop.nsub);
             const long long j = diag ? lpair : lpair / pop.nsub;
             // the random streams are keyed by the GLOBAL pair index, so psi does not depend on how the columns are
@@ -410,6 +415,7 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                     } else if (kind == EV_OBS) {
                         const bool pf = opt.want_ll && !diag && (opt.sde_mode == SDE_PARTICLE_FILTER) && ev_has_value(e.meta);
                         double ysum = 0.0, qsum = 0.0;
+                        double* qv = alt_buf;            // weights, then their running sum, until the ancestors are known
                         int lstat = ST_OK;
                         for (int k = tid; k < np; k += B) {
                             double x[NS];
@@ -524,7 +530,10 @@ __device__ __forceinline__ void psi_sde_kernel_body(const PopView& pop, const do
                     out.ll[(long long)subj + j * out.ld_ll] = ll;
                 }
             }
+            if (tid == 0) next_pair = out.pair_ticket ? (long long)gridDim.x + (long long)atomicAdd(out.pair_ticket, 1ull) : lpair + gridDim.x;
             __syncthreads();
+            lpair = next_pair;
+            __syncthreads();               // (a subject without occasions has no other barrier before the next draw)
             flush_counters(out, cnt);      // per pair: the 32-bit per-thread counters would wrap over a long grid-stride loop
             cnt = Counters{};
         }

@@ -181,6 +181,7 @@ struct OutView {
     double* ll_peers[8];
     int32_t npeers;
     int32_t scratch_in_smem;           // SDE: the particle workspace is the CTA's dynamic shared memory (it fits), not `scratch`
+    unsigned long long* pair_ticket;   // SDE, optional: zeroed per launch; CTAs draw their next pair from it (dynamic balance) instead of striding
     int64_t col_base;                  // global index of local column 0 (column shards / pipelined chunks): error pair = i + (j + col_base) * nsub
 };
 

@@ -6,6 +6,12 @@
 
 namespace pharmsol {
 
+// Particle workspace of one SDE CTA, in doubles (psi_sde.cuh): two state buffers [nstate][np] that swap roles at every
+// resampling — the weights and their running sum live in the first np slots of the idle one — and np 32-bit ancestors.
+inline int64_t sde_workspace_doubles(int nstate, int np) {
+    return (2LL * nstate * np + (np + 1) / 2 + 31) / 32 * 32;
+}
+
 struct LaunchGeometry {
     unsigned grid_x = 1, grid_y = 1, block = 128;
     int warp_tasks = 0;

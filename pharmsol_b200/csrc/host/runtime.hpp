@@ -51,6 +51,8 @@ struct Ctx {
     double* small_host = nullptr;             // pinned staging for latency-bound calls: [0, kSmallIn) support points SoA, then psi
     static constexpr size_t kSmallIn = 64u << 10, kSmallOut = 256u << 10;
     DevBuf spp_rows, spp_soa, out, pred, scratch;
+    DevBuf sde_tickets;      // 64 pair tickets (u64), one per SDE launch in rotation: launches of one context may overlap on different streams
+    unsigned sde_ticket_next = 0;
     // device-resident, replicated psi of a multi-device context (pharmsol_cuda_log_likelihood_matrix_replicated) and the
     // streams / events of the copy-engine push gather: finished column chunks are pushed to the peers over NVLink by
     // cudaMemcpyAsync on these streams while the next chunk is computed

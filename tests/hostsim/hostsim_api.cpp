@@ -129,7 +129,7 @@ int hs_run(void* p, int solver, const double* spp_rows, long nspp, int np, const
         if (!fn) { h->error = "entry " + name + " is not linked into this hostsim module"; return 15; }
         if (h->cm.kind == dsl::ModelKind::Sde) {
             const int np_ = opt.nparticles > 0 ? opt.nparticles : 1;
-            const long long stride = ((2LL * h->cm.state_len + 2) * np_ + 64) / 32 * 32;
+            const long long stride = pharmsol::sde_workspace_doubles(h->cm.state_len, np_);
             std::vector<double> scratch((size_t)stride);
             out.scratch = scratch.data();
             out.scratch_stride = 0;              // one CTA at a time: every CTA reuses the same slab
