@@ -132,18 +132,22 @@ PSI_DEV int erk_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOpts&
     const double rtol = opt.rtol, atol = opt.atol;
     double k[TAB::S][N];
     int iters = 0;
+    if (!(st.t < tstop)) return ST_OK;
+    // Restart work (first slope, first step size) happens at most once per call and only here: inside the step loop both
+    // conditions are invariantly false (k1 is FSAL-carried or kept on a rejection, h stays > 0), and a test left there gets
+    // if-converted into a predicated right-hand side that every step issues (ncu: 7 evaluations per step instead of 6).
+    if (!st.have_k1) {
+        f(st.t, st.y, st.k1);
+        cnt.evals++;
+        st.have_k1 = true;
+    }
+    if (!(st.h > 0.0)) {
+        st.since_restart = 0;
+        if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
+        else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
+    }
     while (st.t < tstop) {
         if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
-        if (!st.have_k1) {
-            f(st.t, st.y, st.k1);
-            cnt.evals++;
-            st.have_k1 = true;
-        }
-        if (!(st.h > 0.0)) {
-            st.since_restart = 0;
-            if (PSI_RESTART_REUSE && st.h_post > 0.0) st.h = st.h_post;
-            else st.h = (opt.h0 > 0.0) ? opt.h0 : initial_step<N>(f, st.t, st.y, st.k1, tstop - st.t, rtol, atol, cnt);
-        }
         const double rem = tstop - st.t;
         const bool last = st.h >= rem;
         const double h = last ? rem : st.h;

@@ -243,7 +243,11 @@ struct Emitter {
     }
 
     Val expr(const ExprP& e, Scope& s) {
-        if ((e->kind == Expr::Binary || e->kind == Expr::Call || e->kind == Expr::Unary || e->kind == Expr::IfElse) && expensive(e) && pair_invariant(e, s)) {
+        // In the right-hand side of an ODE — evaluated 6-7 times per step on the FP64 pipe that bounds those kernels — a
+        // cheap pair-invariant sum / product (`ke + k12`) is hoisted as well: one slot instead of one operation per evaluation.
+        const bool cheap_ok = e->kind == Expr::Binary && c.m.kind == ModelKind::Ode && s.role == Role::Dynamics &&
+                              (e->name == "+" || e->name == "-" || e->name == "*");
+        if ((e->kind == Expr::Binary || e->kind == Expr::Call || e->kind == Expr::Unary || e->kind == Expr::IfElse) && (expensive(e) || cheap_ok) && pair_invariant(e, s)) {
             Val v = expr_raw(e, s);
             if (v.is_const || v.ty != Ty::Real) return v;
             const std::string sl = slot_for(v.code);
@@ -328,6 +332,18 @@ struct Emitter {
             }
             Val x = real(a), y = real(b);
             if (x.is_const && y.is_const) return mkconst(op == "+" ? x.cval + y.cval : op == "-" ? x.cval - y.cval : x.cval * y.cval, Ty::Real);
+            if (op == "*") {
+                // (-a) * b is written -(a * b) — the same value bit for bit — so that the compiler shares a * b with the
+                // other statements that use it (`dx(depot) = -ka * depot`, `dx(central) = ka * depot - ...`)
+                auto negated = [](const ExprP& q, const Val& v) {
+                    return q->kind == Expr::Unary && q->name == "-" && !v.is_const && v.code.size() > 3 && v.code.compare(0, 2, "(-") == 0 && v.code.back() == ')';
+                };
+                const bool nx = negated(e->args[0], x), ny = negated(e->args[1], y);
+                if (nx != ny) {
+                    const std::string xi = nx ? x.code.substr(2, x.code.size() - 3) : x.code, yi = ny ? y.code.substr(2, y.code.size() - 3) : y.code;
+                    Val r; r.code = "(-(" + xi + " * " + yi + "))"; return r;
+                }
+            }
             Val r; r.code = "(" + x.code + " " + op + " " + y.code + ")"; return r;
         }
         if (op == "/") {
@@ -445,11 +461,12 @@ struct Emitter {
                     return t1.empty() ? t2 : t2.empty() ? t1 : "(" + t1 + " + " + t2 + ")";
                 }
                 if (op == "/") {
-                    // (a/b)' = a'/b - a b'/b^2
+                    // (a/b)' = (a' - (a/b) b') / b: one reciprocal of b, shared with the quotient itself, instead of 1/b and 1/b^2
                     const std::string rc = reciprocal(e->args[1], b, s);
-                    std::string t1 = da.empty() ? "" : rc.empty() ? "psi::fdiv(" + da + ", " + b.code + ")" : "(" + da + " * " + rc + ")";
-                    std::string t2 = db.empty() ? "" : "psi::fdiv((" + a.code + " * " + db + "), (" + b.code + " * " + b.code + "))";
-                    return t2.empty() ? t1 : t1.empty() ? "(-" + t2 + ")" : "(" + t1 + " - " + t2 + ")";
+                    if (db.empty()) return rc.empty() ? "psi::fdiv(" + da + ", " + b.code + ")" : "(" + da + " * " + rc + ")";
+                    const std::string q = "psi::fdiv(" + a.code + ", " + b.code + ")";
+                    const std::string num = da.empty() ? "(-(" + q + " * " + db + "))" : "(" + da + " - (" + q + " * " + db + "))";
+                    return "psi::fdiv(" + num + ", " + b.code + ")";
                 }
                 if (op == "^") return deriv_pow(a, b, da, db);
                 return "";
