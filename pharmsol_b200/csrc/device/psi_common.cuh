@@ -79,16 +79,19 @@ PSI_DEV float rsqrt_ftz(float x) {
 #endif
 }
 
-// Reciprocal / quotient to ~1 ulp without the IEEE fix-up path: MUFU.RCP64H seed + two Newton steps (4 DFMA).  CUDA's
+// Reciprocal / quotient to within 1 ulp without the IEEE fix-up path: MUFU.RCP64H seed + one third-order step (3 DFMA).  CUDA's
 // `a / b` costs ~14 instructions plus a divergence-scoped branch to a slow path (ncu on the RODAS4 kernel: FSEL + FSETP +
 // BSSY / BSYNC / BRA are 25 % of the executed instructions, most of them the fix-ups of ~10 divisions per step).  Used
 // where the last bit does not matter: the emitted ODE dynamics / Jacobian (the solver's tolerance dominates), the LU
-// pivots and 1/h.  Zero, infinite or denormal divisors give inf / 0 / inf like the seed does (ftz); NaN propagates.
+// pivots and 1/h.  A zero, infinite or denormal (ftz) divisor gives NaN (0 x inf inside the refinement) where IEEE division
+// gives inf or 0: either way a non-finite right-hand side, which every solver rejects; NaN propagates.
+// The seed is good to 2^-19.9 (measured, scripts/micro/rcp_check.cu: 3e8 log-uniform doubles); with e = 1 - x r the
+// third-order update r (1 + e + e^2) leaves e^3 = 2^-60 before rounding: within 1 ulp of 1/x on every sample, in three
+// dependent FMAs where two Newton steps take four.
 PSI_DEV double rcp_nr(double x) {
-    double r = rcp_approx(x);
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
+    const double r = rcp_approx(x);
+    const double e = fma(-x, r, 1.0);
+    return fma(fma(e, e, e), r, r);
 }
 PSI_DEV double fdiv(double a, double b) { return a * rcp_nr(b); }
 

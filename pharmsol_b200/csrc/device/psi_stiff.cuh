@@ -339,7 +339,7 @@ PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
     while (st.t < tstop) {
         if (++iters > opt.max_steps) return ST_SOLVER_FAILURE;
         if (!st.have_k1) {
-            f(st.t, st.y, st.k1);
+            if (TIME_DEP || !(st.h > 0.0)) f(st.t, st.y, st.k1);      // (the first step size needs it; else see below)
             cnt.evals++;
             st.have_k1 = true;
             if constexpr (TIME_DEP) {       // df/dt at (t_n, y_n) by a forward difference
@@ -363,6 +363,10 @@ PSI_DEV int rodas4_integrate_to(OdeState<N>& st, double tstop, F& f, const RunOp
         const double ihg = ih * (1.0 / g);
         // E = I/(h g) - J, factored in registers (J is re-evaluated instead of stored: a Jacobian costs
         // about one RHS, N*N registers cost occupancy)
+        // f(t_n, y_n) is evaluated next to the Jacobian, also on the attempt after a rejection (1 in 10) where it is already
+        // known: the two share their sub-expressions (the derive block, the Michaelis-Menten reciprocal), which a slope
+        // computed behind the `have_k1` test above cannot
+        if constexpr (!TIME_DEP) f(st.t, st.y, st.k1);
         f.jacobian(st.t, st.y, lu.a);
 #pragma unroll
         for (int i = 0; i < N; ++i)
