@@ -63,6 +63,10 @@ F_RHS = {"c2": 10.0, "c4": 2 * 10 + 8.0}
 # Dopri5 / Tsit5 step.  SURVEY's convention counts 2n(21 + 7 + 7) + 60: 21 a-coefficients, the b row and the error row.
 # The b row IS row 7 of A (FSAL) and one a-coefficient is zero, so the instruction-true figure is 2n(20 + 6 + ...) — both
 # are reported: `frac` follows the survey's convention, `frac_instruction_true` the flop-true count.
+C5_FLOP_PER_EVAL = 14.0
+# warp instructions issued per particle attempt of the SDE kernel (ncu, profiles/r02_final_c5_ncu.txt: smsp__inst_executed
+# 4.84e11 over 8.56e10 thread-attempts, 26.4 of 32 lanes active) — the kernel's real bound is instruction issue
+C5_WARP_INST_PER_ATTEMPT = 5.66
 ERK_STEP = lambda n: 2.0 * n * (21 + 7 + 7) + 60.0
 ERK_STEP_TRUE = lambda n: 2.0 * n * (20 + 6 + 1) + 2.0 * n + 45.0       # stage sums + y + h*acc + error row + weights/controller
 
@@ -80,7 +84,9 @@ def algorithmic_flops(name, npairs, counters, nobs_per_subject, true_count=False
         # RODAS4 / SDIRK: per RHS F_rhs; per Newton iteration one 2x2 solve; per step one Jacobian + LU + stage combinations
         return counters["evals"] * F_RHS["c4"] + counters["newton"] * 30 + (counters["steps"] + counters["rejected"]) * 150
     if name == "c5":
-        return float(counters["evals"]) * 60.0
+        # ncu op counts of the reference stepper (profiles/r02_c5_source_attribution.txt): 14.2 DFMA + 11.0 DMUL + 3.0 DADD
+        # per attempt = 42 flop; the device counts 3 evaluations per attempt
+        return float(counters["evals"]) * C5_FLOP_PER_EVAL
     raise KeyError(name)
 
 
@@ -455,8 +461,16 @@ def measure(env, name, nsub, nspp_total, steps, warmup, tol=1e-6, particles=1000
         roofline["note"] = ("frac follows SURVEY §8d's 2n(21+7+7)+60 flop per step; frac_instruction_true counts the b row once (FSAL: row 7 of A is b) "
                             "and 20 non-zero a-coefficients; ncu op counts (dfma/dadd/dmul) are in profiles/")
     if name == "c5":
-        roofline["note"] = "the SDE kernel is INT/XU-issue bound (Philox + Box-Muller), not FP64: the 60 flop/eval convention is nominal; see particle_evals_per_s"
+        roofline["note"] = ("the SDE kernel is instruction-issue bound (Philox + Box-Muller + the step controller), not FP64: `frac` is the "
+                            "ncu-counted FP64 work against the FP64 peak, `issue` the warp-instruction rate against 4 schedulers x SMs x clock")
         roofline["particle_evals_per_s"] = float(counters["evals"]) / (kernel_ms_avg * 1e-3)
+        attempts = float(counters["steps"] + counters["rejected"])
+        props = torch.cuda.get_device_properties(dev)
+        clock_mhz = getattr(props, "clock_rate", 1965000) / 1e3           # the SM clock the bench's `clocks` samples confirm (1965 MHz)
+        issue_peak = props.multi_processor_count * 4 * clock_mhz * 1e6
+        issue_rate = attempts * C5_WARP_INST_PER_ATTEMPT / (kernel_ms_avg * 1e-3)
+        roofline["issue"] = {"achieved": issue_rate, "peak": issue_peak, "unit": "warp-inst/s", "frac": issue_rate / issue_peak,
+                             "warp_inst_per_attempt": C5_WARP_INST_PER_ATTEMPT, "source": "profiles/r02_final_c5_ncu.txt"}
 
     # ---- end to end through the public host-buffer API -------------------------------------------------
     e2e_rec, e2e_page = None, None
@@ -518,7 +532,7 @@ def slim(rec, keys=("value", "unit", "ms_per_step", "steps", "kernel_ms", "gathe
     out = {k: rec[k] for k in keys if k in rec}
     r = out.get("roofline")
     if r:       # keep the nested records compact: the full counters stay in the headline
-        out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms", "flops_per_pair", "traffic", "particle_evals_per_s", "note") if k in r}
+        out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms", "flops_per_pair", "traffic", "particle_evals_per_s", "issue", "note") if k in r}
     return out
 
 

@@ -47,8 +47,11 @@ PSI_DEV float powf_fast(float x, float p) {
 // norms of the explicit pairs need it once per component per step, and DSETP / FP64 selects would add to the pipe that
 // bounds those kernels.  A NaN input gives a NaN-or-larger pattern; the step is then rejected by the non-finite error test.
 PSI_DEV double max_abs(double a, double b) {
-    const long long ia = __double_as_longlong(a) & 0x7fffffffffffffffLL, ib = __double_as_longlong(b) & 0x7fffffffffffffffLL;
-    return __longlong_as_double(ia > ib ? ia : ib);
+    // on the 32-bit halves: a 64-bit `& 0x7fff...` is recognised as fabs and comes back as an FP64-pipe DADD
+    const unsigned int ah = (unsigned int)__double2hiint(a) & 0x7fffffffu, bh = (unsigned int)__double2hiint(b) & 0x7fffffffu;
+    const unsigned int al = (unsigned int)__double2loint(a), bl = (unsigned int)__double2loint(b);
+    const bool a_wins = ah > bh || (ah == bh && al > bl);
+    return __hiloint2double((int)(a_wins ? ah : bh), (int)(a_wins ? al : bl));
 }
 
 // min / max of two doubles of which at most one is negative (and neither is -0), on the integer pipe: such doubles order

@@ -29,6 +29,9 @@ struct double2 { double x, y; };
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
+inline int __double2loint(double d) { return (int)(unsigned int)(__double_as_longlong(d) & 0xffffffffLL); }
+inline double __hiloint2double(int hi, int lo) { return __longlong_as_double((long long)(((unsigned long long)(unsigned int)hi << 32) | (unsigned int)lo)); }
 inline float __powf(float a, float b) { return std::pow(a, b); }
 inline float __logf(float a) { return std::log(a); }
 inline void __sincosf(float a, float* s, float* c) { *s = std::sin(a); *c = std::cos(a); }
