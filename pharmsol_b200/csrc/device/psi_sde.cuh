@@ -100,8 +100,10 @@ PSI_DEV double philox_uniform(const Philox& ph, unsigned int c0, unsigned int c1
 
 // ---- block reductions / scan (blockDim.x == 128 => 4 warps) ---------------------------------------
 PSI_DEV double block_sum(double v, double* smem4) {
+#ifndef PSI_HOST_SIM      // (the host build runs one thread per CTA: there are no other lanes to add)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#endif
     const int w = threadIdx.x >> 5;
     __syncthreads();
     if ((threadIdx.x & 31) == 0) smem4[w] = v;

@@ -164,6 +164,28 @@ def test_sde_kernel_source_runs_single_threaded(HS, oracle):
     assert np.abs(a - b).max() <= 1e-3 * np.abs(a - c).max()
 
 
+@pytest.mark.parametrize("key,mode", [("mean_prediction", 0), ("particle_filter", 1)])
+def test_reference_adaptive_stepper_matches_the_oracle_fixture(HS, key, mode):
+    """The reference's adaptive Euler-Maruyama path (sde/em.rs:134-167) of the device source on the host: normals carried
+    across the 4-attempt cycles, the out-of-line infusion window, the integer-pipe clamps.  Eight (subject, support point)
+    pairs of the `box64` case of tests/golden/sde_c5_oracle.json (what tests/test_gpu_sde_parity.py checks on the device
+    for all 64), both likelihood modes, 128 particles, 24 seeds: seed-averaged ll within 3.5 SE pooled, 4.5 SE per pair."""
+    from benches import workloads as W
+    from conftest import golden
+    case = next(c for c in golden("sde_c5_oracle")["cases"] if c["name"] == "box64")
+    w = W.make("c5", nsub=case["nsub"], nspp=case["nspp"], particles=case["particles"])
+    ns, nc, nseed = 2, 4, 24
+    hs = HS(w["dsl"]).set_subjects(w["subjects"][:ns])
+    ems = _ems(w)
+    g = np.stack([hs.run(w["support_points"][:nc], ems, seed=41000 + s, particles=case["particles"], sde_mode=mode, em_mode=0)[0] for s in range(nseed)])
+    ref = case[key]
+    mean_o, var_o = np.array(ref["mean"])[:ns, :nc], np.array(ref["var"])[:ns, :nc]
+    assert np.isfinite(g).all()
+    se = np.sqrt(g.var(axis=0, ddof=1) / nseed + var_o / case["nseed"])
+    z = (g.mean(axis=0) - mean_o) / se
+    assert abs(z.mean()) * np.sqrt(z.size) <= 3.5 and np.abs(z).max() <= 4.5, z
+
+
 def test_bdf_restart_at_an_emptied_compartment(HS):
     """Regression: pair (subject 286, column 172) of the C4 workload.  An infusion switches on at t = 12 h when the
     Michaelis-Menten compartment has emptied to ~atol: Hairer's starting step comes out at ~1e-13.  The BDF driver used
