@@ -186,6 +186,27 @@ def test_reference_adaptive_stepper_matches_the_oracle_fixture(HS, key, mode):
     assert abs(z.mean()) * np.sqrt(z.size) <= 3.5 and np.abs(z).max() <= 4.5, z
 
 
+def test_two_state_particle_filter_matches_the_oracle(HS, oracle):
+    """The reference's own particle-filter fixture (tests/test_pf.rs:8-59): two states, so an attempt of the adaptive
+    stepper needs 6 normals and a particle's attempts run in cycles of 2 over 3 Philox blocks (psi_sde.cuh: the carry
+    pattern differs from the one-state C5 model).  Seed-averaged particle-filter ll vs the restated reference, 3.5 SE,
+    at three parameter values."""
+    c = FX.PF_TEST
+    np_, nseed = 192, 40
+    spp = np.array([[0.6], [1.0], [1.6]])
+    om = oracle.Model("pf_test", particles=np_)
+    od = oracle.Data([oracle.Subject(c["ops"], "a")])
+    oe = oracle.ErrorModels([c["error_model"]])
+    o = np.stack([om.log_likelihood_matrix(od, spp, oe, seed=900 + s, sde_mode=1)[0] for s in range(nseed)])
+    hs = HS(c["dsl"]).set_subjects([("a", c["ops"])])
+    em = [(1, c["error_model"][1], c["error_model"][2])]
+    g = np.stack([hs.run(spp, em, seed=77000 + s, particles=np_, sde_mode=1, em_mode=0)[0][0] for s in range(nseed)])
+    assert np.isfinite(o).all() and np.isfinite(g).all()
+    se = np.sqrt(g.var(axis=0, ddof=1) / nseed + o.var(axis=0, ddof=1) / nseed)
+    z = (g.mean(axis=0) - o.mean(axis=0)) / se
+    assert np.abs(z).max() <= 3.5, (z, g.mean(axis=0), o.mean(axis=0))
+
+
 def test_bdf_restart_at_an_emptied_compartment(HS):
     """Regression: pair (subject 286, column 172) of the C4 workload.  An infusion switches on at t = 12 h when the
     Michaelis-Menten compartment has emptied to ~atol: Hairer's starting step comes out at ~1e-13.  The BDF driver used
