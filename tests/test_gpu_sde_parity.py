@@ -64,6 +64,29 @@ def test_baseline_slice_1000_particles_seed_averaged_vs_oracle(ps, key, mode):
     _check(g, case[key], case["nseed"])
 
 
+def test_two_state_particle_filter_matches_the_oracle(ps, oracle):
+    """The reference's own particle-filter fixture (tests/test_pf.rs:8-59), two states: an attempt of the adaptive stepper
+    needs 6 normals, so a particle's attempts run in cycles of 2 over 3 Philox blocks — a different carry pattern from the
+    one-state C5 model.  Seed-averaged particle-filter ll vs the restated reference within 3.5 SE at three parameter values
+    (tests/test_hostsim.py runs the same comparison with the device source compiled for the host)."""
+    import fixtures as FX
+    c = FX.PF_TEST
+    np_, nseed = 192, 48
+    spp = np.array([[0.6], [1.0], [1.6]])
+    om = oracle.Model("pf_test", particles=np_)
+    od = oracle.Data([oracle.Subject(c["ops"], "a")])
+    oe = oracle.ErrorModels([c["error_model"]])
+    o = np.stack([om.log_likelihood_matrix(od, spp, oe, seed=900 + s, sde_mode=1)[0] for s in range(nseed)])
+    eq = ps.Equation.from_dsl(c["dsl"]).with_particles(np_).with_mode(ps.SdeMode.ParticleFilter).with_stepper(ps.EmMode.ReferenceAdaptive)
+    em = ps.AssayErrorModels().add("cp", ps.AssayErrorModel.additive(ps.ErrorPoly(*c["error_model"][2]), 0.0))
+    data = ps.Data([ps.Subject("a", c["ops"])])
+    g = np.stack([ps.log_likelihood_matrix(eq.with_seed(77000 + s), data, spp, em)[0] for s in range(nseed)])
+    assert np.isfinite(o).all() and np.isfinite(g).all()
+    se = np.sqrt(g.var(axis=0, ddof=1) / nseed + o.var(axis=0, ddof=1) / nseed)
+    z = (g.mean(axis=0) - o.mean(axis=0)) / se
+    assert np.abs(z).max() <= 3.5, (z, g.mean(axis=0), o.mean(axis=0))
+
+
 def test_fp32_and_fp64_noise_give_the_same_likelihood(ps):
     """The device draws FP32 Box-Muller normals from 24-bit uniforms by default where the reference samples an f64
     Normal (sde/em.rs:104-120).  With PCU_SDE_NORMALS_FP64 the same Philox words feed an FP64 Box-Muller on 32-bit
