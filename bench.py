@@ -183,7 +183,9 @@ def config_dict(name, w, nsub, nspp_per_gpu, nspp_total, world, tol, particles, 
         cfg.update(solver=WORKLOADS[name]["solver"], rtol=tol, atol=tol)
     if w["kind"] == "sde":
         cfg.update(particles=particles, sde_mode="particle filter (SDE::estimate_log_likelihood, sde/mod.rs:526-577)",
-                   stepper="reference adaptive Euler-Maruyama (sde/em.rs:134-167)")
+                   stepper="reference adaptive Euler-Maruyama (sde/em.rs:134-167)",
+                   noise="standard normals by FP32 Box-Muller from Philox4x32-10 words (library default, DESIGN.md §4); state, drift, "
+                         "diffusion, weights and likelihood arithmetic in FP64")
     return cfg
 
 
